@@ -1,0 +1,110 @@
+/*
+ * skychunk.h -- C ABI of the B200 chunk-processing stage (libskychunk.so).
+ *
+ * Drop-in boundary for the per-chunk hot path of Skyplane's gateway.  The reference has no FFI
+ * (it is pure Python); these entry points replace, for one batch of chunks, the two calls
+ *     data = lz4.frame.compress(data)          skyplane/gateway/operators/gateway_operator.py:358-361
+ *     m = hashlib.md5(); m.update(b); digest   skyplane/obj_store/s3_interface.py:181-192
+ * and hand back exactly what the sender needs for its wire header (gateway_operator.py:367-372):
+ * the frame bytes, their length, and the 16-byte digest for Chunk.md5_hash (skyplane/chunk.py:21).
+ *
+ * Conventions: plain pointers and sizes, no exceptions, 0 = success / negative = error code.
+ * The caller owns every host buffer; the library owns device memory, streams and events.
+ * One sky_ctx per process per GPU; calls on one ctx are not thread-safe (the reference runs one
+ * process per worker, gateway_operator.py:66-70).  A ctx must be created in the process that uses
+ * it (after fork), never inherited.
+ *
+ * Output format: one LZ4 frame per chunk that lz4.frame.decompress (gateway_receiver.py:196)
+ * restores bit-exactly: magic, FLG=0x68 (v01, independent blocks, content size), BD=0x40 (64 KiB),
+ * u64le content size, header checksum, blocks (bit 31 set = stored raw), EndMark.  A zero-length
+ * chunk yields the 11-byte frame liblz4 itself emits (content size omitted).
+ */
+#ifndef SKYCHUNK_H
+#define SKYCHUNK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SKY_API __attribute__((visibility("default")))
+#else
+#define SKY_API
+#endif
+
+#define SKY_ABI_VERSION 1
+
+/* error codes */
+#define SKY_OK 0
+#define SKY_E_INVALID (-1)   /* bad argument (null pointer, misaligned device pointer, n == 0 ...) */
+#define SKY_E_NOGPU (-2)     /* no CUDA device / driver: there is NO CPU fallback */
+#define SKY_E_CUDA (-3)      /* a CUDA call failed; see sky_last_error() */
+#define SKY_E_CAPACITY (-4)  /* batch exceeds what the ctx was created for, or dst_cap < sky_frame_bound() */
+#define SKY_E_BUSY (-5)      /* all slots hold un-waited tickets */
+#define SKY_E_TICKET (-6)    /* unknown / already consumed ticket */
+#define SKY_E_NOMEM (-7)
+
+/* stage selection for sky_process_device (0 = both) */
+#define SKY_F_LZ4 1u
+#define SKY_F_MD5 2u
+/* keep the SM sub-partition that hosts an MD5 warp free of LZ4 warps */
+#define SKY_F_MD5_EXCLUSIVE 4u
+
+typedef struct sky_ctx sky_ctx;
+
+SKY_API const char *sky_strerror(int code);
+SKY_API const char *sky_last_error(const sky_ctx *ctx); /* detail of the last SKY_E_CUDA on this ctx */
+SKY_API int sky_abi_version(void);
+SKY_API int sky_device_count(int *count);
+
+/* Worst-case frame bytes for an n-byte chunk: 15 + n + 4*ceil(n/65536) + 4 (11 when n == 0). */
+SKY_API uint64_t sky_frame_bound(uint64_t n);
+
+/* Create a context on `device` able to hold batches of up to max_chunks chunks totalling
+ * max_batch_bytes input bytes.  n_slots >= 1 batches may be in flight through sky_submit at once
+ * (each slot owns an input slab, an output slab and a stream); n_slots == 0 creates a ctx for
+ * sky_process_device only (no slabs). */
+SKY_API int sky_ctx_create(int device, uint64_t max_batch_bytes, uint32_t max_chunks, uint32_t n_slots, sky_ctx **out);
+SKY_API int sky_ctx_destroy(sky_ctx *ctx);
+
+/* Page-locked host memory for staging chunk bytes (cudaHostAlloc, portable). */
+SKY_API void *sky_pinned_alloc(uint64_t bytes);
+SKY_API int sky_pinned_free(void *p);
+
+/* ---- host-buffer path (what GatewayOperator.process uses) -------------------------------------
+ * sky_submit: asynchronously copies n chunks host->device, runs the fused kernel, and stages the
+ *   per-chunk sizes and digests back.  src[i]/src_len[i] = chunk bytes; dst[i]/dst_cap[i] = where
+ *   the frame goes (dst_cap[i] >= sky_frame_bound(src_len[i])).  All host buffers must stay valid
+ *   until sky_wait returns.  Pinned buffers make the copies truly asynchronous.
+ * sky_wait: blocks until the batch is done, copies each frame device->host (exact length), and
+ *   fills out_len[n], md5[16*n].  kernel_ms (optional) = device time of the fused kernel. */
+SKY_API int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
+               const uint64_t *dst_cap, uint64_t *ticket);
+SKY_API int sky_wait(sky_ctx *ctx, uint64_t ticket, uint64_t *out_len, uint8_t *md5, float *kernel_ms);
+
+/* ---- device-resident path (kernel metric; inputs already in HBM) ------------------------------
+ * Chunk i is d_src[src_off[i] .. +src_len[i]) ; its frame is written at d_dst + dst_off[i]
+ * (capacity dst_cap[i] >= sky_frame_bound(src_len[i])).  src_off/dst_off must be multiples of 16
+ * and both regions must be readable/writable up to the next multiple of 16.  `stream` is a
+ * cudaStream_t (NULL = the ctx's own stream).  Synchronous: returns after the results are on the
+ * host.  flags: SKY_F_* (0 = LZ4 + MD5). */
+SKY_API int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, const uint64_t *src_off, const uint64_t *src_len,
+                       void *d_dst, const uint64_t *dst_off, const uint64_t *dst_cap, uint32_t flags, void *stream,
+                       uint64_t *out_len, uint8_t *md5, float *kernel_ms);
+
+/* Device-memory helpers so a host without torch can drive the device path. */
+SKY_API int sky_device_alloc(sky_ctx *ctx, uint64_t bytes, void **dptr);
+SKY_API int sky_device_free(sky_ctx *ctx, void *dptr);
+SKY_API int sky_memcpy_h2d(sky_ctx *ctx, void *dptr, const void *host, uint64_t bytes);
+SKY_API int sky_memcpy_d2h(sky_ctx *ctx, void *host, const void *dptr, uint64_t bytes);
+
+/* Number of kernel launches issued through this ctx so far (bench.py's gpu_launches). */
+SKY_API uint64_t sky_launch_count(const sky_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKYCHUNK_H */

@@ -1,0 +1,263 @@
+// lz4.cuh -- warp-per-block LZ4 block compressor for sm_100a.
+//
+// Replaces, per 64 KiB block, what lz4.frame.compress(data) does inside
+// skyplane/gateway/operators/gateway_operator.py:358-361 (liblz4's level-0 "fast" compressor:
+// single-candidate hash table, greedy, skip acceleration).  The GPU formulation:
+//   * one warp owns one independent 64 KiB block (frame flag B.Indep, so no cross-block state);
+//   * the match table is 4096 x u16 block positions in shared memory (8 KiB per warp);
+//   * each iteration the 32 lanes probe 32 cursor positions (stride = LZ4's skip step, which grows
+//     by one every 64 failed probes), the lowest matching lane wins (greedy = reference order),
+//     the match is extended backwards/forwards cooperatively, and the sequence is emitted.
+//   * blocks that do not shrink are stored raw (bit 31 of the block header), like LZ4F_makeBlock.
+// Output is a standard LZ4 block: decodable by lz4.frame.decompress (gateway_receiver.py:196).
+#pragma once
+#include <stdint.h>
+
+namespace sky {
+
+constexpr uint32_t kBlock = 65536;       // BD = 0x40
+constexpr uint32_t kSlot = kBlock + 4;   // worst-case block footprint in the frame (header + raw data)
+constexpr uint32_t kHashLog = 12;
+constexpr uint32_t kHashSize = 1u << kHashLog;
+constexpr uint32_t kMinMatch = 4;
+constexpr uint32_t kMfLimit = 12;        // a match must start >= 12 bytes before the block end
+constexpr uint32_t kLastLiterals = 5;    // the last 5 bytes are always literals
+constexpr uint32_t kSkipTrigger = 6;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- unaligned little-endian 32-bit read from global memory (base 4-byte aligned) --------------
+__device__ __forceinline__ uint32_t load32(const uint8_t *base, uint32_t pos) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (pos & ~3u));
+    const uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, (pos & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t lz4_hash(uint32_t v) { return (v * 2654435761u) >> (32 - kHashLog); }
+
+// ---- warp copy: dst and src arbitrarily aligned; regions disjoint, or dst < src (forward move) ----
+// Over-reads at most 3 bytes past src+n (inside the same 4-byte word group); never over-writes.
+__device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint32_t n, unsigned lane) {
+    if (n < 64) {
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t k = base + lane;
+            uint8_t b = 0;
+            if (k < n) b = src[k];
+            __syncwarp();
+            if (k < n) dst[k] = b;
+        }
+        return;
+    }
+    const uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;  // < 16 <= n
+    uint8_t hb = 0;
+    if (lane < head) hb = src[lane];
+    __syncwarp();
+    if (lane < head) dst[lane] = hb;
+    dst += head;
+    src += head;
+    n -= head;
+    const uint32_t nvec = n >> 4;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst);
+    for (uint32_t base = 0; base < nvec; base += 32) {
+        const uint32_t k = base + lane;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (k < nvec) {
+            const uint32_t *q = sw + 4 * (size_t)k;
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+            const uint32_t w4 = sh ? q[4] : 0u;
+            o.x = __funnelshift_r(w0, w1, sh);
+            o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh);
+            o.w = __funnelshift_r(w3, w4, sh);
+        }
+        __syncwarp();  // every lane has its source words before any lane overwrites (forward move)
+        if (k < nvec) dv[k] = o;
+    }
+    const uint32_t done = nvec << 4, tail = n & 15u;
+    uint8_t tb = 0;
+    if (lane < tail) tb = src[done + lane];
+    __syncwarp();
+    if (lane < tail) dst[done + lane] = tb;
+}
+
+// ---- XXH32 of the frame descriptor (2 or 10 bytes), for the header checksum byte -----------------
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
+__device__ __forceinline__ uint32_t xxh32_small(const uint8_t *p, uint32_t len) {  // len < 16, seed 0
+    constexpr uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    uint32_t h = P5 + len;
+    uint32_t i = 0;
+    for (; i + 4 <= len; i += 4) {
+        const uint32_t v = p[i] | (p[i + 1] << 8) | (p[i + 2] << 16) | ((uint32_t)p[i + 3] << 24);
+        h = rotl32(h + v * P3, 17) * P4;
+    }
+    for (; i < len; i++) h = rotl32(h + p[i] * P5, 11) * P1;
+    h ^= h >> 15;
+    h *= P2;
+    h ^= h >> 13;
+    h *= P3;
+    h ^= h >> 16;
+    return h;
+}
+
+// Writes the frame header for an n-byte chunk at dst; returns its size (15, or 7 when n == 0).
+// Single thread.
+__device__ __forceinline__ uint32_t write_frame_header(uint8_t *dst, uint64_t n) {
+    uint8_t d[10];
+    d[1] = 0x40;  // BD: 64 KiB blocks
+    dst[0] = 0x04; dst[1] = 0x22; dst[2] = 0x4D; dst[3] = 0x18;
+    if (n == 0) {
+        d[0] = 0x60;  // v01 | B.Indep ; content size omitted (0 means "unknown" to LZ4F)
+        dst[4] = d[0]; dst[5] = d[1];
+        dst[6] = (uint8_t)(xxh32_small(d, 2) >> 8);
+        return 7;
+    }
+    d[0] = 0x68;  // v01 | B.Indep | C.Size
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[2 + i] = (uint8_t)(n >> (8 * i));
+#pragma unroll
+    for (int i = 0; i < 10; i++) dst[4 + i] = d[i];
+    dst[14] = (uint8_t)(xxh32_small(d, 10) >> 8);
+    return 15;
+}
+
+// ---- sequence emission ----------------------------------------------------------------------------
+// Bytes a sequence with `ll` literals and match length `ml` (>= 4, or 0 for the final literal run) needs.
+__device__ __forceinline__ uint32_t seq_bytes(uint32_t ll, uint32_t ml) {
+    uint32_t s = 1 + ll + (ll >= 15 ? (ll - 15) / 255 + 1 : 0);
+    if (ml) s += 2 + ((ml - 4) >= 15 ? (ml - 4 - 15) / 255 + 1 : 0);
+    return s;
+}
+
+// Emits token, literal-length bytes, literals, offset, match-length bytes.  All lanes call it with
+// warp-uniform arguments; returns the new output cursor.
+__device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const uint8_t *src, uint32_t anchor, uint32_t ll,
+                                            uint32_t ml, uint32_t offset, unsigned lane) {
+    const uint32_t mcode = ml ? ml - kMinMatch : 0;
+    if (lane == 0) out[op] = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mcode < 15 ? mcode : 15));
+    op += 1;
+    if (ll >= 15) {
+        const uint32_t r = ll - 15, n255 = r / 255;
+        for (uint32_t k = lane; k < n255; k += 32) out[op + k] = 255;
+        if (lane == 0) out[op + n255] = (uint8_t)(r - n255 * 255);
+        op += n255 + 1;
+    }
+    warp_copy(out + op, src + anchor, ll, lane);
+    op += ll;
+    if (ml) {
+        if (lane == 0) {
+            out[op] = (uint8_t)offset;
+            out[op + 1] = (uint8_t)(offset >> 8);
+        }
+        op += 2;
+        if (mcode >= 15) {
+            const uint32_t r = mcode - 15, n255 = r / 255;
+            for (uint32_t k = lane; k < n255; k += 32) out[op + k] = 255;
+            if (lane == 0) out[op + n255] = (uint8_t)(r - n255 * 255);
+            op += n255 + 1;
+        }
+    }
+    return op;
+}
+
+// ---- the block compressor -------------------------------------------------------------------------
+// src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: where compressed
+// bytes may be written (capacity L bytes), ht: this warp's 4096-entry table.
+// Returns the compressed size (1..L-1), or 0 if the block does not shrink (caller stores it raw).
+__device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict__ src, uint32_t L, uint8_t *__restrict__ out,
+                                                      uint16_t *ht, unsigned lane) {
+    // clear the table: 8 KiB = 32 lanes x 16 x 16 B
+    {
+        uint4 *t4 = reinterpret_cast<uint4 *>(ht);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < (int)(kHashSize * 2 / 16 / 32); k++) t4[k * 32 + lane] = z;
+    }
+    __syncwarp();
+
+    uint32_t ip = 0, anchor = 0, op = 0;
+    const uint32_t limit = L - 1;  // accept only csize <= L-1 (LZ4F_makeBlock passes dstCapacity = srcSize-1)
+
+    if (L >= kMfLimit + 1) {
+        const uint32_t mflimit = L - kMfLimit;        // last position a match may start at
+        const uint32_t matchlimit = L - kLastLiterals;  // matches end at or before this
+        uint32_t nprobe = 1u << kSkipTrigger;           // LZ4: searchMatchNb = acceleration << skipTrigger
+        while (ip <= mflimit) {
+            const uint32_t step = nprobe >> kSkipTrigger;
+            const uint32_t pos = ip + lane * step;
+            const bool valid = pos <= mflimit;
+            uint32_t v = 0, h = 0, cand = 0;
+            if (valid) {
+                v = load32(src, pos);
+                h = lz4_hash(v);
+                cand = ht[h];
+            }
+            __syncwarp();
+            if (valid) ht[h] = (uint16_t)pos;
+            __syncwarp();
+            const bool hit = valid && cand < pos && load32(src, cand) == v;
+            const unsigned hits = __ballot_sync(kFull, hit);
+            if (hits == 0) {
+                ip += 32 * step;
+                nprobe += 32;
+                continue;
+            }
+            const int m = __ffs(hits) - 1;
+            uint32_t mpos = __shfl_sync(kFull, pos, m);
+            uint32_t mcand = __shfl_sync(kFull, cand, m);
+
+            // backward extension ("catch up")
+            {
+                uint32_t room = min(mpos - anchor, mcand);
+                while (room) {
+                    const bool eq = lane < room && src[mpos - 1 - lane] == src[mcand - 1 - lane];
+                    const unsigned em = __ballot_sync(kFull, eq);
+                    const uint32_t nb = (em == kFull) ? 32u : (uint32_t)(__ffs(~em) - 1);
+                    mpos -= nb;
+                    mcand -= nb;
+                    room -= nb;
+                    if (nb < 32) break;
+                }
+            }
+            // forward extension, 4 bytes per lane per round
+            uint32_t mlen = kMinMatch;
+            {
+                const uint32_t maxlen = matchlimit - mpos;  // >= 7
+                for (;;) {
+                    const uint32_t o = mlen + lane * 4;
+                    uint32_t cnt = 0;
+                    if (o < maxlen) {
+                        const uint32_t x = load32(src, mpos + o) ^ load32(src, mcand + o);
+                        cnt = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+                        cnt = min(cnt, maxlen - o);
+                    }
+                    const unsigned fullm = __ballot_sync(kFull, cnt == 4);
+                    if (fullm == kFull) {
+                        mlen += 128;
+                        continue;
+                    }
+                    const int f = __ffs(~fullm) - 1;
+                    mlen += 4 * f + __shfl_sync(kFull, cnt, f);
+                    break;
+                }
+            }
+            const uint32_t ll = mpos - anchor;
+            const uint32_t need = seq_bytes(ll, mlen);
+            if (op + need + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
+            op = emit_seq(out, op, src, anchor, ll, mlen, mpos - mcand, lane);
+            ip = mpos + mlen;
+            anchor = ip;
+            nprobe = 1u << kSkipTrigger;
+            // like LZ4_putPosition(ip-2): remember a position inside the match tail
+            if (lane == 0 && ip <= mflimit + 2 && ip >= 2) ht[lz4_hash(load32(src, ip - 2))] = (uint16_t)(ip - 2);
+            __syncwarp();
+        }
+    }
+    // last literals
+    const uint32_t last = L - anchor;
+    if (op + seq_bytes(last, 0) > limit) return 0;
+    op = emit_seq(out, op, src, anchor, last, 0, 0, lane);
+    return op;
+}
+
+}  // namespace sky

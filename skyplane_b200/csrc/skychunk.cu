@@ -1,0 +1,517 @@
+// skychunk.cu -- fused LZ4-frame + MD5 chunk stage for B200 (sm_100a) and its C ABI (include/skychunk.h).
+//
+// One persistent kernel per batch, one CTA per SM, 16 warps per CTA, roles per warp:
+//   * MD5 warps  : 32 chunks per warp, lane = chunk (md5.cuh).  Statically spread: MD5 slot
+//                  s = warp*gridDim + blockIdx takes groups s, s+4*gridDim, ... so 32 groups land on
+//                  32 different SMs.  An MD5 chain is latency bound (3 dependent ALU ops per step).
+//   * LZ4 warps  : one 64 KiB block per work item (lz4.cuh), claimed from a global atomic counter in
+//                  row-major order (block row j of every chunk, then row j+1 ...).
+// Output placement (single pass, no compaction kernel): block j is compressed into its WORST-CASE
+// slot (15 + j*65540) inside the chunk's output region; when the predecessor publishes where block
+// j really starts (per-chunk chain word, release/acquire), the warp writes the 4-byte block header and,
+// only if the start moved, slides its bytes left (forward move) or -- for a stored block -- copies the
+// input straight to the final place.  Incompressible data therefore costs exactly one read of the input
+// and one write of the output.  The last block's warp writes the EndMark and the frame length.
+//
+// Host side: sky_ctx owns a stream, pinned + device metadata arrays, and (optionally) per-slot input /
+// output slabs for the host-buffer path (H2D -> kernel -> D2H on one stream per slot).
+// There is NO CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/skychunk.h"
+#include "lz4.cuh"
+#include "md5.cuh"
+
+namespace sky {
+
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMd5WarpsPerCta = 4;  // warps 0..3 (one per SM sub-partition) may host MD5 groups
+constexpr uint32_t kSmemBytes = kWarps * kHashSize * 2;  // 128 KiB: one 8 KiB table / MD5 ring per warp
+constexpr int kOffBits = 40;
+constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
+
+struct ChunkDesc {
+    const uint8_t *src;  // 16-byte aligned
+    uint8_t *dst;        // 16-byte aligned
+    uint64_t len;
+    uint32_t nblk;
+    uint32_t pad;
+};
+
+struct Params {
+    const ChunkDesc *chunks;
+    const uint32_t *md5_order;  // chunk indices, longest first, padded with 0xffffffff to 32*n_groups
+    uint64_t *chain;            // per chunk: (next block index << 40) | frame offset of that block
+    uint64_t *out_len;          // per chunk frame length
+    uint8_t *md5_out;           // 16 bytes per chunk
+    uint32_t *counters;         // [0] = LZ4 work counter
+    uint32_t n_chunks;
+    uint32_t n_groups;
+    uint32_t rows;  // max(1, max nblk)
+    uint32_t flags;
+};
+
+__device__ __forceinline__ uint64_t ld_acquire(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(uint64_t *p, uint64_t v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// One LZ4 work item: block j of chunk c.
+__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint16_t *ht, unsigned lane) {
+    const ChunkDesc cd = p.chunks[c];
+    if (cd.nblk == 0) {
+        if (j == 0 && lane == 0) {  // empty chunk: 7-byte header + EndMark
+            const uint32_t h = write_frame_header(cd.dst, 0);
+            cd.dst[h] = cd.dst[h + 1] = cd.dst[h + 2] = cd.dst[h + 3] = 0;
+            p.out_len[c] = h + 4;
+        }
+        return;
+    }
+    if (j >= cd.nblk) return;
+    if (j == 0 && lane == 0) write_frame_header(cd.dst, cd.len);
+
+    const uint64_t boff = (uint64_t)j * kBlock;
+    const uint32_t L = (uint32_t)min((uint64_t)kBlock, cd.len - boff);
+    const uint8_t *src = cd.src + boff;
+    const uint64_t slot = 15 + (uint64_t)j * kSlot;  // worst-case position of this block's header
+    uint8_t *out = cd.dst + slot + 4;
+
+    const uint32_t csize = lz4_compress_block(src, L, out, ht, lane);
+    __syncwarp();
+
+    // wait for the predecessor to publish where this block starts
+    uint64_t st = 0;
+    if (lane == 0) {
+        const uint64_t *cw = p.chain + c;
+        unsigned ns = 32;
+        while (((st = ld_acquire(cw)) >> kOffBits) != j) {
+            __nanosleep(ns);
+            if (ns < 1024) ns <<= 1;
+        }
+    }
+    st = __shfl_sync(kFull, st, 0);
+    const uint64_t off = st & kOffMask;  // <= slot
+    uint8_t *hdr = cd.dst + off;
+    uint32_t bsize, hword;
+    if (csize) {
+        bsize = csize;
+        hword = csize;
+        if (off != slot) warp_copy(hdr + 4, out, csize, lane);  // slide left (dst < src)
+    } else {
+        bsize = L;
+        hword = L | 0x80000000u;
+        warp_copy(hdr + 4, src, L, lane);  // stored block: straight from the input
+    }
+    if (lane < 4) hdr[lane] = (uint8_t)(hword >> (8 * lane));
+    const uint64_t end = off + 4 + bsize;
+    if (j + 1 == cd.nblk) {
+        if (lane < 4) cd.dst[end + lane] = 0;  // EndMark
+        if (lane == 0) p.out_len[c] = end + 4;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *my = smem + warp * (kHashSize * 2);
+
+    const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
+    const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
+
+    if (do_md5 && warp < kMd5WarpsPerCta) {
+        for (uint32_t g = warp * gridDim.x + blockIdx.x; g < p.n_groups; g += md5_slots) {
+            const uint32_t c = p.md5_order[g * 32 + lane];
+            const bool active = c != 0xffffffffu;
+            const uint8_t *src = nullptr;
+            uint64_t len = 0;
+            if (active) {
+                src = p.chunks[c].src;
+                len = p.chunks[c].len;
+            }
+            md5_warp(reinterpret_cast<uint32_t *>(my), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16, lane);
+            __syncwarp();
+        }
+    }
+    if (!do_lz4) return;
+    if (do_md5 && (p.flags & SKY_F_MD5_EXCLUSIVE)) {
+        // keep the sub-partition of an MD5 warp free: warps sharing (warp & 3) with an MD5-hosting
+        // warp of this CTA do no LZ4 work.
+        const unsigned sub = warp & 3;
+        if (sub * gridDim.x + blockIdx.x < p.n_groups) return;
+    }
+    const uint32_t total = p.rows * p.n_chunks;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(p.counters, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= total) break;
+        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint16_t *>(my), lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace sky
+
+// ======================================================================================= host side
+using namespace sky;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    // per-batch metadata (device + pinned host mirrors)
+    ChunkDesc *h_desc = nullptr, *d_desc = nullptr;
+    uint32_t *h_order = nullptr, *d_order = nullptr;
+    uint64_t *h_chain = nullptr, *d_chain = nullptr;
+    uint64_t *h_outlen = nullptr, *d_outlen = nullptr;
+    uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
+    uint32_t *d_counters = nullptr;
+    // in-flight ticket
+    bool busy = false;
+    uint64_t ticket = 0;
+    uint32_t n = 0;
+    std::vector<void *> dst;
+    std::vector<uint64_t> out_off;
+};
+
+struct sky_ctx {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t max_bytes = 0;
+    uint32_t max_chunks = 0;
+    uint64_t in_cap = 0, out_cap = 0;
+    std::vector<Slot> slots;  // slots[0] doubles as the metadata holder for sky_process_device
+    uint64_t next_ticket = 1;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define CK(ctx, call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            char b_[512];                                                                  \
+            snprintf(b_, sizeof b_, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (ctx) (ctx)->err = b_;                                                      \
+            g_err = b_;                                                                    \
+            return SKY_E_CUDA;                                                             \
+        }                                                                                  \
+    } while (0)
+
+extern "C" {
+
+const char *sky_strerror(int code) {
+    switch (code) {
+    case SKY_OK: return "ok";
+    case SKY_E_INVALID: return "invalid argument";
+    case SKY_E_NOGPU: return "no CUDA device available (this library has no CPU fallback)";
+    case SKY_E_CUDA: return "CUDA error";
+    case SKY_E_CAPACITY: return "capacity exceeded";
+    case SKY_E_BUSY: return "all slots busy";
+    case SKY_E_TICKET: return "unknown ticket";
+    case SKY_E_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+const char *sky_last_error(const sky_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+int sky_abi_version(void) { return SKY_ABI_VERSION; }
+
+int sky_device_count(int *count) {
+    if (!count) return SKY_E_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        *count = 0;
+        g_err = cudaGetErrorString(e);
+        return SKY_E_NOGPU;
+    }
+    *count = n;
+    return SKY_OK;
+}
+
+uint64_t sky_frame_bound(uint64_t n) {
+    if (n == 0) return 11;
+    return 15 + n + 4 * ((n + kBlock - 1) / kBlock) + 4;
+}
+
+static uint64_t round16(uint64_t x) { return (x + 15) & ~15ull; }
+
+static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
+    const size_t nc = max_chunks, ng = (nc + 31) / 32 * 32;
+    CK(ctx, cudaMallocHost(&s.h_desc, nc * sizeof(ChunkDesc)));
+    CK(ctx, cudaMallocHost(&s.h_order, ng * sizeof(uint32_t)));
+    CK(ctx, cudaMallocHost(&s.h_chain, nc * sizeof(uint64_t)));
+    CK(ctx, cudaMallocHost(&s.h_outlen, nc * sizeof(uint64_t)));
+    CK(ctx, cudaMallocHost(&s.h_md5, nc * 16));
+    CK(ctx, cudaMalloc(&s.d_desc, nc * sizeof(ChunkDesc)));
+    CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
+    CK(ctx, cudaMalloc(&s.d_outlen, nc * sizeof(uint64_t)));
+    CK(ctx, cudaMalloc(&s.d_md5, nc * 16));
+    CK(ctx, cudaMalloc(&s.d_counters, 64));
+    CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreate(&s.ev_k0));
+    CK(ctx, cudaEventCreate(&s.ev_k1));
+    return SKY_OK;
+}
+
+static void free_slot(Slot &s) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
+    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_outlen); cudaFree(s.d_md5); cudaFree(s.d_counters);
+    cudaFree(s.d_in); cudaFree(s.d_out);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+int sky_ctx_create(int device, uint64_t max_batch_bytes, uint32_t max_chunks, uint32_t n_slots, sky_ctx **out) {
+    if (!out || max_chunks == 0) return SKY_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (sky_device_count(&ndev) != SKY_OK) return SKY_E_NOGPU;
+    if (device < 0 || device >= ndev) return SKY_E_INVALID;
+    sky_ctx *ctx = new (std::nothrow) sky_ctx();
+    if (!ctx) return SKY_E_NOMEM;
+    ctx->device = device;
+    ctx->max_bytes = max_batch_bytes;
+    ctx->max_chunks = max_chunks;
+    auto fail = [&](int rc) {
+        g_err = ctx->err;
+        for (auto &s : ctx->slots) free_slot(s);
+        delete ctx;
+        return rc;
+    };
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return fail(SKY_E_CUDA); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return fail(SKY_E_CUDA); }
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaFuncSetAttribute(sky_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e) + " (built for sm_100a only)";
+        return fail(SKY_E_CUDA);
+    }
+    const uint32_t ns = n_slots ? n_slots : 1;
+    ctx->slots.resize(ns);
+    // every chunk is placed at a 16-byte aligned offset; frames need bound(len) each
+    ctx->in_cap = round16(max_batch_bytes) + 16ull * max_chunks + 256;
+    ctx->out_cap = max_batch_bytes + (uint64_t)max_chunks * (64 + 4 * 2) + 4 * (max_batch_bytes / kBlock + 1) + 256;
+    for (uint32_t i = 0; i < ns; i++) {
+        int rc = alloc_meta(ctx, ctx->slots[i], max_chunks);
+        if (rc != SKY_OK) return fail(rc);
+        if (n_slots) {
+            e = cudaMalloc(&ctx->slots[i].d_in, ctx->in_cap);
+            if (e == cudaSuccess) e = cudaMalloc(&ctx->slots[i].d_out, ctx->out_cap);
+            if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(slab): ") + cudaGetErrorString(e); return fail(SKY_E_NOMEM); }
+        }
+    }
+    *out = ctx;
+    return SKY_OK;
+}
+
+int sky_ctx_destroy(sky_ctx *ctx) {
+    if (!ctx) return SKY_E_INVALID;
+    cudaSetDevice(ctx->device);
+    for (auto &s : ctx->slots) free_slot(s);
+    delete ctx;
+    return SKY_OK;
+}
+
+void *sky_pinned_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        g_err = cudaGetErrorString(e);
+        return nullptr;
+    }
+    return p;
+}
+int sky_pinned_free(void *p) {
+    if (!p) return SKY_OK;
+    return cudaFreeHost(p) == cudaSuccess ? SKY_OK : SKY_E_CUDA;
+}
+
+// Fills the slot's metadata for a batch and enqueues: meta H2D, counter reset, fused kernel, results D2H.
+static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, const uint8_t *d_src, const uint64_t *src_off,
+                        const uint64_t *src_len, uint8_t *d_dst, const uint64_t *dst_off, uint32_t flags) {
+    if ((flags & (SKY_F_LZ4 | SKY_F_MD5)) == 0) flags |= SKY_F_LZ4 | SKY_F_MD5;
+    uint32_t rows = 1;
+    for (uint32_t i = 0; i < n; i++) {
+        ChunkDesc &d = s.h_desc[i];
+        d.src = d_src + src_off[i];
+        d.dst = d_dst + dst_off[i];
+        d.len = src_len[i];
+        const uint64_t nb = (src_len[i] + kBlock - 1) / kBlock;
+        if (nb >= (1ull << 24)) return SKY_E_CAPACITY;
+        d.nblk = (uint32_t)nb;
+        d.pad = 0;
+        rows = std::max(rows, d.nblk);
+        s.h_chain[i] = 15;  // block 0 starts right after the 15-byte frame header
+    }
+    if ((uint64_t)rows * n >= 0xffffffffull) return SKY_E_CAPACITY;
+    // MD5 lane assignment: longest chunks first so a warp's 32 lanes carry similar lengths
+    const uint32_t ng = (n + 31) / 32;
+    std::iota(s.h_order, s.h_order + n, 0u);
+    std::stable_sort(s.h_order, s.h_order + n, [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+    for (uint32_t i = n; i < ng * 32; i++) s.h_order[i] = 0xffffffffu;
+
+    CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(s.d_order, s.h_order, ng * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(s.d_chain, s.h_chain, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
+    CK(ctx, cudaMemsetAsync(s.d_outlen, 0, n * sizeof(uint64_t), st));
+    CK(ctx, cudaMemsetAsync(s.d_md5, 0, n * 16, st));
+
+    Params p;
+    p.chunks = s.d_desc;
+    p.md5_order = s.d_order;
+    p.chain = s.d_chain;
+    p.out_len = s.d_outlen;
+    p.md5_out = s.d_md5;
+    p.counters = s.d_counters;
+    p.n_chunks = n;
+    p.n_groups = ng;
+    p.rows = rows;
+    p.flags = flags;
+    CK(ctx, cudaEventRecord(s.ev_k0, st));
+    sky_fused_kernel<<<ctx->sm_count, kThreads, kSmemBytes, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(s.ev_k1, st));
+    ctx->launches++;
+    CK(ctx, cudaMemcpyAsync(s.h_outlen, s.d_outlen, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaMemcpyAsync(s.h_md5, s.d_md5, n * 16, cudaMemcpyDeviceToHost, st));
+    return SKY_OK;
+}
+
+int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, const uint64_t *src_off, const uint64_t *src_len,
+                       void *d_dst, const uint64_t *dst_off, const uint64_t *dst_cap, uint32_t flags, void *stream,
+                       uint64_t *out_len, uint8_t *md5, float *kernel_ms) {
+    if (!ctx || n == 0 || !src_off || !src_len || !dst_off || !dst_cap || !d_dst) return SKY_E_INVALID;
+    if (n > ctx->max_chunks) return SKY_E_CAPACITY;
+    if ((reinterpret_cast<uintptr_t>(d_src) & 15) || (reinterpret_cast<uintptr_t>(d_dst) & 15)) return SKY_E_INVALID;
+    for (uint32_t i = 0; i < n; i++) {
+        if ((src_off[i] & 15) || (dst_off[i] & 15)) return SKY_E_INVALID;
+        if (dst_cap[i] < sky_frame_bound(src_len[i])) return SKY_E_CAPACITY;
+        if (src_len[i] && !d_src) return SKY_E_INVALID;
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    if (s.busy) return SKY_E_BUSY;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    int rc = launch_batch(ctx, s, st, n, (const uint8_t *)d_src, src_off, src_len, (uint8_t *)d_dst, dst_off, flags);
+    if (rc != SKY_OK) return rc;
+    CK(ctx, cudaStreamSynchronize(st));
+    if (out_len) memcpy(out_len, s.h_outlen, n * sizeof(uint64_t));
+    if (md5) memcpy(md5, s.h_md5, (size_t)n * 16);
+    if (kernel_ms) CK(ctx, cudaEventElapsedTime(kernel_ms, s.ev_k0, s.ev_k1));
+    return SKY_OK;
+}
+
+int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
+               const uint64_t *dst_cap, uint64_t *ticket) {
+    if (!ctx || n == 0 || !src || !src_len || !dst || !dst_cap || !ticket) return SKY_E_INVALID;
+    if (n > ctx->max_chunks) return SKY_E_CAPACITY;
+    Slot *sp = nullptr;
+    for (auto &s : ctx->slots)
+        if (!s.busy && s.d_in) { sp = &s; break; }
+    if (!sp) return ctx->slots[0].d_in ? SKY_E_BUSY : SKY_E_INVALID;
+    Slot &s = *sp;
+    CK(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint64_t> in_off(n), out_off(n);
+    uint64_t ip = 0, op = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (src_len[i] && !src[i]) return SKY_E_INVALID;
+        if (!dst[i] || dst_cap[i] < sky_frame_bound(src_len[i])) return SKY_E_CAPACITY;
+        in_off[i] = ip;
+        out_off[i] = op;
+        ip += round16(src_len[i]);
+        op += round16(sky_frame_bound(src_len[i]));
+    }
+    if (ip > ctx->in_cap || op > ctx->out_cap) return SKY_E_CAPACITY;
+    for (uint32_t i = 0; i < n; i++)
+        if (src_len[i]) CK(ctx, cudaMemcpyAsync(s.d_in + in_off[i], src[i], src_len[i], cudaMemcpyHostToDevice, s.stream));
+    int rc = launch_batch(ctx, s, s.stream, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), 0);
+    if (rc != SKY_OK) return rc;
+    s.busy = true;
+    s.ticket = ctx->next_ticket++;
+    s.n = n;
+    s.dst.assign(dst, dst + n);
+    s.out_off.swap(out_off);
+    *ticket = s.ticket;
+    return SKY_OK;
+}
+
+int sky_wait(sky_ctx *ctx, uint64_t ticket, uint64_t *out_len, uint8_t *md5, float *kernel_ms) {
+    if (!ctx) return SKY_E_INVALID;
+    Slot *sp = nullptr;
+    for (auto &s : ctx->slots)
+        if (s.busy && s.ticket == ticket) { sp = &s; break; }
+    if (!sp) return SKY_E_TICKET;
+    Slot &s = *sp;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(s.stream));  // sizes + digests are on the host now
+    for (uint32_t i = 0; i < s.n; i++)
+        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaStreamSynchronize(s.stream));
+    if (out_len) memcpy(out_len, s.h_outlen, s.n * sizeof(uint64_t));
+    if (md5) memcpy(md5, s.h_md5, (size_t)s.n * 16);
+    if (kernel_ms) CK(ctx, cudaEventElapsedTime(kernel_ms, s.ev_k0, s.ev_k1));
+    s.busy = false;
+    return SKY_OK;
+}
+
+int sky_device_alloc(sky_ctx *ctx, uint64_t bytes, void **dptr) {
+    if (!ctx || !dptr) return SKY_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SKY_E_NOMEM; }
+    return SKY_OK;
+}
+int sky_device_free(sky_ctx *ctx, void *dptr) {
+    if (!ctx) return SKY_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(dptr));
+    return SKY_OK;
+}
+int sky_memcpy_h2d(sky_ctx *ctx, void *dptr, const void *host, uint64_t bytes) {
+    if (!ctx) return SKY_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
+    return SKY_OK;
+}
+int sky_memcpy_d2h(sky_ctx *ctx, void *host, const void *dptr, uint64_t bytes) {
+    if (!ctx) return SKY_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpy(host, dptr, bytes, cudaMemcpyDeviceToHost));
+    return SKY_OK;
+}
+
+uint64_t sky_launch_count(const sky_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

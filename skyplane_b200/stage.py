@@ -1,0 +1,160 @@
+"""ChunkStage: the host side of the B200 compress+hash stage (pinned staging + libskychunk).
+
+This is what replaces, for a batch of chunks, the reference's two per-chunk CPU calls
+(``lz4.frame.compress`` at skyplane/gateway/operators/gateway_operator.py:359 and the
+``hashlib.md5`` loop at skyplane/obj_store/s3_interface.py:181-192).  Chunk bytes are read
+straight into page-locked host memory, shipped to HBM, compressed + hashed by one fused kernel
+launch, and the frames land in page-locked memory ready for ``sock.sendall``.
+
+No CPU fallback: constructing a ChunkStage without a CUDA device raises SkyChunkError.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Union
+
+from skyplane_b200 import native
+
+BytesLike = Union[bytes, bytearray, memoryview]
+
+
+@dataclass
+class StageResult:
+    """What the sender needs for one chunk (gateway_operator.py:367-372)."""
+
+    frame: memoryview  # LZ4 frame bytes (view into the slot's pinned output; valid until the slot is reused)
+    md5: bytes  # 16 raw bytes == hashlib.md5(chunk).digest()
+    raw_len: int  # WireProtocolHeader.raw_data_len
+    comp_len: int  # WireProtocolHeader.data_len (before optional encryption)
+
+    def frame_bytes(self) -> bytes:
+        return bytes(self.frame)
+
+
+class _Slot:
+    def __init__(self, in_bytes: int, out_bytes: int):
+        self.inp = native.PinnedBuffer(in_bytes)
+        self.out = native.PinnedBuffer(out_bytes)
+        self.reset()
+
+    def reset(self):
+        self.in_off: List[int] = []
+        self.lens: List[int] = []
+        self.out_off: List[int] = []
+        self.in_used = 0
+        self.out_used = 0
+        self.ticket: Optional[int] = None
+
+    def reserve(self, n: int) -> memoryview:
+        """Reserve room for an n-byte chunk; returns the writable pinned view to fill."""
+        bound = native.frame_bound(n)
+        if self.in_used + native.round16(n) > self.inp.nbytes or self.out_used + native.round16(bound) > self.out.nbytes:
+            raise native.SkyChunkError(native.SKY_E_CAPACITY, "batch exceeds the stage's staging buffers")
+        off = self.in_used
+        self.in_off.append(off)
+        self.lens.append(n)
+        self.out_off.append(self.out_used)
+        self.in_used += native.round16(n)
+        self.out_used += native.round16(bound)
+        return self.inp.view[off : off + n]
+
+
+class ChunkStage:
+    def __init__(self, device: int = 0, max_batch_bytes: int = 256 << 20, max_chunks: int = 256, n_slots: int = 2):
+        if n_slots < 1:
+            raise ValueError("n_slots must be >= 1")
+        self.ctx = native.Context(device, max_batch_bytes, max_chunks, n_slots)
+        self.max_chunks = max_chunks
+        self.max_batch_bytes = max_batch_bytes
+        in_bytes = native.round16(max_batch_bytes) + 16 * max_chunks
+        out_bytes = max_batch_bytes + 4 * (max_batch_bytes // 65536 + 1) + 64 * max_chunks
+        self._slots = [_Slot(in_bytes, out_bytes) for _ in range(n_slots)]
+        self._free = list(self._slots)
+
+    # ------------------------------------------------------------------ async API
+    def begin(self) -> _Slot:
+        """Take a free staging slot (raises SKY_E_BUSY if every slot has an un-collected batch)."""
+        if not self._free:
+            raise native.SkyChunkError(native.SKY_E_BUSY, "collect() an earlier batch first")
+        s = self._free.pop()
+        s.reset()
+        return s
+
+    def fits(self, slot: _Slot, n: int) -> bool:
+        return (
+            len(slot.lens) < self.max_chunks
+            and slot.in_used + native.round16(n) <= slot.inp.nbytes
+            and slot.out_used + native.round16(native.frame_bound(n)) <= slot.out.nbytes
+        )
+
+    def add_bytes(self, slot: _Slot, data: BytesLike) -> int:
+        mv = memoryview(data).cast("B")
+        dst = slot.reserve(mv.nbytes)
+        if mv.nbytes:
+            dst[:] = mv
+        return len(slot.lens) - 1
+
+    def add_file(self, slot: _Slot, path: os.PathLike, length: int) -> int:
+        """Read exactly `length` bytes of a chunk file into pinned memory (gateway_operator.py:350-352)."""
+        dst = slot.reserve(length)
+        got = 0
+        with open(path, "rb", buffering=0) as f:
+            while got < length:
+                r = f.readinto(dst[got:])
+                if not r:
+                    break
+                got += r
+            extra = f.read(1) if got == length else b""
+        if got != length or extra:
+            slot.in_off.pop(); slot.lens.pop(); slot.out_off.pop()
+            raise AssertionError(f"chunk file {path} has size != {length}")
+        return len(slot.lens) - 1
+
+    def launch(self, slot: _Slot) -> _Slot:
+        if not slot.lens:
+            raise ValueError("empty batch")
+        base_in, base_out = slot.inp.addr, slot.out.addr
+        src = [base_in + o for o in slot.in_off]
+        dst = [base_out + o for o in slot.out_off]
+        caps = [native.frame_bound(n) for n in slot.lens]
+        slot.ticket = self.ctx.submit(src, slot.lens, dst, caps)
+        return slot
+
+    def collect(self, slot: _Slot) -> List[StageResult]:
+        out_lens, digests, self.last_kernel_ms = self.ctx.wait(slot.ticket)
+        res = [
+            StageResult(frame=slot.out.view[o : o + cl], md5=dg, raw_len=n, comp_len=cl)
+            for o, cl, dg, n in zip(slot.out_off, out_lens, digests, slot.lens)
+        ]
+        slot.ticket = None
+        self._free.append(slot)
+        return res
+
+    # ------------------------------------------------------------------ sync convenience
+    def process(self, chunks: Sequence[BytesLike]) -> List[StageResult]:
+        """Compress + hash a list of in-memory chunks; frames are returned as independent bytes."""
+        out: List[StageResult] = []
+        i = 0
+        while i < len(chunks):
+            slot = self.begin()
+            j = i
+            while j < len(chunks) and self.fits(slot, memoryview(chunks[j]).nbytes):
+                self.add_bytes(slot, chunks[j])
+                j += 1
+            if j == i:
+                self._free.append(slot)
+                raise native.SkyChunkError(native.SKY_E_CAPACITY, f"chunk of {memoryview(chunks[i]).nbytes} bytes exceeds max_batch_bytes")
+            self.launch(slot)
+            for r in self.collect(slot):
+                out.append(StageResult(frame=memoryview(bytes(r.frame)), md5=r.md5, raw_len=r.raw_len, comp_len=r.comp_len))
+            i = j
+        return out
+
+    def close(self):
+        self.ctx.close()
+        for s in self._slots:
+            s.inp.close()
+            s.out.close()
+        self._slots = []
+        self._free = []

@@ -1,0 +1,67 @@
+"""GPU test of the plugin boundary: GatewayCompressHash workers inside the queue harness
+(BASELINE config 1/4 shape, small): chunk files -> GatewayQueue -> forked worker -> GPU -> output queue."""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+
+import pytest
+
+import oracle
+import oracle.reflib as ref
+from skyplane_b200 import synth
+from skyplane_b200.chunk import WireProtocolHeader
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+DRIVER = r"""
+import json, sys
+from pathlib import Path
+from skyplane_b200.harness import run_stream
+base = Path(sys.argv[1]); n_req = int(sys.argv[2]); workers = int(sys.argv[3])
+files = sorted((base / "pool").glob("*.bin"), key=lambda p: int(p.stem))
+lens = [p.stat().st_size for p in files]
+res = run_stream(base / "chunks", files, lens, n_req, n_workers=workers, max_batch_chunks=8, max_batch_bytes=64 << 20, keep_frames=True)
+print("RESULT " + json.dumps(res))
+"""
+
+
+def _run(base: Path, n_req: int, workers: int):
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, "-c", DRIVER, str(base), str(n_req), str(workers)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.loads(line[len("RESULT "):])
+
+
+def test_operator_in_queue_harness():
+    base = Path(tempfile.mkdtemp(prefix="skyb200_test_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
+    try:
+        (base / "pool").mkdir()
+        pool = [synth.random_chunk(0, 8 << 20), synth.silesia_like_chunk(1, 8 << 20), b"", b"x" * 13, synth.silesia_like_chunk(2, (1 << 20) + 77),
+                synth.random_chunk(5, 65536)]
+        for k, d in enumerate(pool):
+            (base / "pool" / f"{k}.bin").write_bytes(d)
+        n_req = 40
+        res = _run(base, n_req, workers=2)
+        assert len(res["records"]) == n_req and res["bytes"] == sum(len(pool[i % len(pool)]) for i in range(n_req))
+        assert res["status"].get("complete") == n_req and res["status"].get("in_progress") == n_req and res["status"].get("registered") == n_req
+        assert res["uncompressed_bytes"] == res["bytes"] and 0 < res["compressed_bytes"] < res["bytes"]
+        for rec in res["records"]:
+            data = pool[rec["pool_index"]]
+            assert rec["md5"] == hashlib.md5(data).hexdigest()
+            frame = Path(rec["frame_path"]).read_bytes()
+            assert oracle.lz4f_decode(frame, len(data)) == data
+            assert ref.lz4f_decompress(frame, len(data)) == data  # what the destination gateway does (gateway_receiver.py:196)
+            # the three header fields the sender derives (gateway_operator.py:367-372)
+            hdr = WireProtocolHeader(rec["chunk_id"], len(frame), rec["raw_len"], True, 0)
+            back = WireProtocolHeader.from_bytes(hdr.to_bytes())
+            assert back.data_len == len(frame) and back.raw_data_len == len(data) and back.is_compressed
+    finally:
+        import shutil
+
+        shutil.rmtree(base, ignore_errors=True)

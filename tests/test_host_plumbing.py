@@ -1,0 +1,276 @@
+"""CPU tests of the host side: reference-compatible types, queues, chunk store, the operator plugin
+loop, the C-ABI surface, loud failure without a GPU, and the N>1 sharding logic over gloo."""
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import pickle
+import queue
+import re
+import socket
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import pytest
+
+from skyplane_b200 import native
+from skyplane_b200.chunk import Chunk, ChunkRequest, ChunkState, WireProtocolHeader
+from skyplane_b200.chunk_store import ChunkStore
+from skyplane_b200.gateway_queue import GatewayANDQueue, GatewayQueue
+from skyplane_b200.operators import GatewayCompressHash, GatewayOperator
+from skyplane_b200.sharding import shard_indices, shard_of_chunk_id
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# ------------------------------------------------------------------ chunk.py parity with the reference
+def test_wire_header_matches_reference_bytes(golden):
+    g = golden["wire_headers"]
+    assert WireProtocolHeader.length_bytes() == g["length_bytes"] == 53
+    assert WireProtocolHeader.magic_hex() == g["magic"]
+    assert WireProtocolHeader.protocol_version() == g["version"]
+    for case in g["headers"]:
+        h = WireProtocolHeader(**case["fields"])
+        assert h.to_bytes().hex() == case["bytes_hex"]
+        assert WireProtocolHeader.from_bytes(bytes.fromhex(case["bytes_hex"])) == h
+
+
+def test_chunk_dicts_match_reference(golden):
+    g = golden["wire_headers"]
+    chunk = Chunk.from_dict(g["chunk_as_dict"])
+    assert chunk.as_dict() == g["chunk_as_dict"]
+    req = ChunkRequest(chunk=chunk, src_region="aws:us-east-1", dst_region="gcp:us-west1")
+    assert req.as_dict() == g["chunk_request_as_dict"]
+    hdr = chunk.to_wire_header(n_chunks_left_on_socket=5, wire_length=100, raw_wire_length=200, is_compressed=True)
+    assert hdr.to_bytes().hex() == g["to_wire_header_hex"]
+    assert [s.name for s in ChunkState] == g["chunk_states"]
+    assert ChunkRequest.from_dict(g["chunk_as_dict"]).chunk == chunk
+    assert ChunkState.from_str("COMPLETE") is ChunkState.complete and ChunkState.registered < ChunkState.complete
+
+
+def test_wire_header_errors_and_socket():
+    h = WireProtocolHeader("ab" * 16, 10, 20, True, 1)
+    raw = bytearray(h.to_bytes())
+    raw[0] ^= 0xFF
+    with pytest.raises(ValueError, match="magic"):
+        WireProtocolHeader.from_bytes(bytes(raw))
+    raw = bytearray(h.to_bytes())
+    raw[11] = 2
+    with pytest.raises(ValueError, match="version"):
+        WireProtocolHeader.from_bytes(bytes(raw))
+    a, b = socket.socketpair()
+    try:
+        h.to_socket(a)
+        assert WireProtocolHeader.from_socket(b) == h
+    finally:
+        a.close()
+        b.close()
+
+
+def test_md5_hash_json_and_pickle_paths():
+    c = Chunk("s", "d", "00" * 16, 5, md5_hash=bytes(range(16)))
+    with pytest.raises(TypeError):
+        json.dumps(c.as_dict())  # the reference's JSON hop cannot carry raw bytes
+    back = Chunk.from_json_dict(json.loads(json.dumps(c.as_json_dict())))
+    assert back == c
+    assert pickle.loads(pickle.dumps(ChunkRequest(c))).chunk.md5_hash == bytes(range(16))
+
+
+# ------------------------------------------------------------------ queues + store
+def test_gateway_queue_semantics():
+    q = GatewayQueue(maxsize=4)
+    q.register_handle("op")
+    assert q.get_handles() == ["op"]
+    with pytest.raises(queue.Empty):
+        q.get_nowait("op")
+    for i in range(3):
+        q.put(i)
+    time.sleep(0.05)
+    assert q.get_batch_nowait(2) == [0, 1]
+    assert q.get_batch_nowait(8) == [2]
+    aq = GatewayANDQueue()
+    aq.register_handle("a")
+    aq.register_handle("b")
+    aq.put("x")
+    time.sleep(0.05)
+    assert aq.get_nowait("a") == "x" and aq.get_nowait("b") == "x"
+    with pytest.raises(ValueError):
+        aq.put_nowait("y")
+
+
+def test_chunk_store(tmp_path):
+    (tmp_path / "stale.chunk").write_bytes(b"x")
+    cs = ChunkStore(tmp_path)
+    assert not (tmp_path / "stale.chunk").exists()
+    q = GatewayQueue()
+    cs.add_partition("0", q)
+    with pytest.raises(ValueError):
+        cs.add_partition("0", q)
+    req = ChunkRequest(Chunk("s", "d", "ab" * 16, 3, partition_id="0"))
+    size, ok = cs.add_chunk_request(req)
+    assert ok
+    rec = cs.chunk_status_queue.get(timeout=2)
+    assert rec["state"] == "registered" and rec["chunk_id"] == "ab" * 16
+    with pytest.raises(ValueError):
+        cs.add_chunk_request(ChunkRequest(Chunk("s", "d", "cd" * 16, 3, partition_id="nope")))
+    assert cs.get_chunk_file_path("ab" * 16) == tmp_path / ("ab" * 16 + ".chunk")
+    assert cs.get_compressed_file_path("ab" * 16).name.endswith(".chunk.lz4")
+    cs.log_chunk_state(req, ChunkState.complete, worker_id=1, operator_handle="h", metadata={"compressed_size_bytes": 1})
+    rec = cs.chunk_status_queue.get(timeout=2)
+    assert rec["state"] == "complete" and rec["compressed_size_bytes"] == 1 and rec["handle"] == "h"
+    assert cs.remaining_bytes() > 0
+
+
+# ------------------------------------------------------------------ operator plugin loop (no GPU involved)
+class _Upper(GatewayOperator):
+    """Toy operator: succeeds on the 2nd attempt for chunk ids starting with 'ff', raises for 'ee'."""
+
+    def process(self, chunk_req, *args):
+        cid = chunk_req.chunk.chunk_id
+        if cid.startswith("ee"):
+            raise RuntimeError("boom")
+        if cid.startswith("ff") and chunk_req.chunk.mime_type is None:
+            chunk_req.chunk.mime_type = "retried"
+            return False
+        chunk_req.chunk.dest_key = chunk_req.chunk.dest_key.upper()
+        return True
+
+
+def _drain(q, n, timeout=10.0):
+    out, t0 = [], time.time()
+    while len(out) < n and time.time() - t0 < timeout:
+        try:
+            out.append(q.get_nowait())
+        except queue.Empty:
+            time.sleep(0.01)
+    return out
+
+
+def test_operator_worker_loop_conventions(tmp_path):
+    cs = ChunkStore(tmp_path)
+    qin, qout = GatewayQueue(), GatewayQueue()
+    err_ev, err_q = mp.Event(), mp.Queue()
+    op = _Upper("up", "test:r", qin, qout, err_ev, err_q, cs, n_processes=2)
+    op.start_workers()
+    try:
+        ids = ["%032x" % i for i in range(6)] + ["ff" + "0" * 30]
+        for cid in ids:
+            qin.put(ChunkRequest(Chunk("k", "dst", cid, 1, partition_id="0")))
+        got = _drain(qout, len(ids))
+        assert sorted(r.chunk.chunk_id for r in got) == sorted(ids)
+        assert all(r.chunk.dest_key == "DST" for r in got)
+        assert [r for r in got if r.chunk.chunk_id.startswith("ff")][0].chunk.mime_type == "retried"  # False -> re-queued
+        states = {}
+        t0 = time.time()
+        while time.time() - t0 < 5 and sum(len(v) for v in states.values()) < 2 * len(ids) + 1:
+            try:
+                rec = cs.chunk_status_queue.get(timeout=0.2)
+                states.setdefault(rec["chunk_id"], []).append(rec["state"])
+            except queue.Empty:
+                pass
+        assert all(v[0] == "in_progress" and v[-1] == "complete" for v in states.values())
+        qin.put(ChunkRequest(Chunk("k", "dst", "ee" + "0" * 30, 1)))
+        t0 = time.time()
+        while not err_ev.is_set() and time.time() - t0 < 5:
+            time.sleep(0.01)
+        assert err_ev.is_set() and "boom" in err_q.get(timeout=2)  # exception -> gateway-wide stop
+    finally:
+        op.stop_workers()
+
+
+# ------------------------------------------------------------------ C ABI surface
+def test_header_and_library_symbols_agree():
+    hdr = (ROOT / "include" / "skychunk.h").read_text()
+    declared = set(re.findall(r"SKY_API[^;]*?\b(sky_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(native.ABI_SYMBOLS)
+    lib = native.lib()  # builds with nvcc if missing (cross-compiles without a GPU)
+    for name in native.ABI_SYMBOLS:
+        assert hasattr(lib, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", str(native.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (sky_[a-z0-9_]+)", out))
+    assert exported == declared
+    assert lib.sky_abi_version() == 1
+
+
+def test_frame_bound_and_strerror_without_gpu():
+    import oracle
+
+    for n in (0, 1, 65535, 65536, 65537, 8 << 20, (64 << 20) + 3):
+        want = 11 if n == 0 else oracle.lz4f_bound(n)
+        assert native.frame_bound(n) == want
+    assert native.frame_bound(8 << 20) == 8389139
+    assert b"no CUDA device" in native.lib().sky_strerror(native.SKY_E_NOGPU)
+
+
+def test_library_carries_sm100a_code():
+    out = subprocess.run(["cuobjdump", "-lelf", str(native.LIB_PATH)], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(native.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_product_path_fails_loudly_without_gpu(tmp_path):
+    with pytest.raises(native.SkyChunkError) as e:
+        native.Context(0, 1 << 20, 4, 1)
+    assert e.value.code == native.SKY_E_NOGPU
+    from skyplane_b200.stage import ChunkStage
+
+    with pytest.raises(native.SkyChunkError):
+        ChunkStage()
+    cs = ChunkStore(tmp_path)
+    op = GatewayCompressHash("ch", "test:r", GatewayQueue(), None, mp.Event(), mp.Queue(), cs)
+    cid = "ab" * 16
+    cs.get_chunk_file_path(cid).write_bytes(b"hello")
+    with pytest.raises(native.SkyChunkError):  # no silent CPU path
+        op.process(ChunkRequest(Chunk("s", "d", cid, 5)))
+
+
+def test_product_package_never_imports_the_oracle():
+    for p in (ROOT / "skyplane_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h"):
+            text = p.read_text()
+            assert "import oracle" not in text and "from oracle" not in text and "skyoracle" not in text, p
+
+
+# ------------------------------------------------------------------ sharding + N>1 reduction over gloo
+def test_shard_rules():
+    assert shard_indices(10, 0, 4) == [0, 4, 8] and shard_indices(10, 3, 4) == [3, 7]
+    all_idx = sorted(i for r in range(8) for i in shard_indices(1024, r, 8))
+    assert all_idx == list(range(1024))
+    assert shard_of_chunk_id("0" * 31 + "9", 8) == 1
+    with pytest.raises(ValueError):
+        shard_indices(4, 4, 4)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from skyplane_b200.sharding import max_over_ranks, shard_indices, sum_over_ranks
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = shard_indices(11, rank, world)
+        elapsed = 1.0 + rank  # rank 1 is "slower"
+        q.put((rank, mine, max_over_ranks(elapsed), sum_over_ranks(len(mine))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_max_over_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(60)
+    assert res[0][1] == [0, 2, 4, 6, 8, 10] and res[1][1] == [1, 3, 5, 7, 9]
+    assert res[0][2] == res[1][2] == 2.0  # MAX over ranks
+    assert res[0][3] == res[1][3] == 11.0  # every unit counted once
