@@ -330,7 +330,7 @@ def run_gpu(args):
     if not args.no_e2e:
         sub = min(args.e2e_batch, n_chunks)
         n_sub = (n_chunks + sub - 1) // sub
-        slots = 3
+        slots = args.e2e_slots
         ectx = native.Context(local, sub * stride_in, sub, slots)
         pool_n = min(64, n_chunks)
         pin_in = native.PinnedBuffer(pool_n * stride_in)
@@ -414,7 +414,8 @@ def main():
     ap.add_argument("--chunks", type=int, default=1024, help="chunks per GPU per step")
     ap.add_argument("--chunk-mib", type=int, default=8)
     ap.add_argument("--workload", choices=["random", "silesia"], default="random")
-    ap.add_argument("--e2e-batch", type=int, default=128, help="chunks per sky_submit call")
+    ap.add_argument("--e2e-batch", type=int, default=256, help="chunks per sky_submit call")
+    ap.add_argument("--e2e-slots", type=int, default=4, help="sky_submit batches in flight")
     ap.add_argument("--ref-chunks", type=int, default=0, help="chunks per step of the reference arm (default: --chunks)")
     ap.add_argument("--cpu-chunks", type=int, default=1024, help="chunks in the cpu_baseline sample")
     ap.add_argument("--md5-exclusive", action="store_true")

@@ -52,6 +52,8 @@ extern "C" {
 #define SKY_F_MD5 2u
 /* keep the SM sub-partition that hosts an MD5 warp free of LZ4 warps */
 #define SKY_F_MD5_EXCLUSIVE 4u
+/* do not pace LZ4 work to the MD5 lanes' progress (pacing lets the lanes read the input from L2) */
+#define SKY_F_NO_PACING 8u
 
 typedef struct sky_ctx sky_ctx;
 

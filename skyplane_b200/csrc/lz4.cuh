@@ -81,6 +81,55 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
     if (lane < tail) dst[done + lane] = tb;
 }
 
+// ---- warp copy for DISJOINT regions whose source is kernel-read-only input (ld.global.nc), 4 x 16 B in
+// flight per lane.  src 16-byte aligned; dst arbitrary.
+__device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t n, unsigned lane) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    if (mis == 0) {
+        const uint4 *sv = reinterpret_cast<const uint4 *>(src);
+        uint4 *dv = reinterpret_cast<uint4 *>(dst);
+        const uint32_t nvec = n >> 4;
+        uint32_t k = lane;
+        for (; k + 96 < nvec; k += 128) {
+            const uint4 a = __ldg(sv + k), b = __ldg(sv + k + 32), c = __ldg(sv + k + 64), d = __ldg(sv + k + 96);
+            dv[k] = a; dv[k + 32] = b; dv[k + 64] = c; dv[k + 96] = d;
+        }
+        for (; k < nvec; k += 32) dv[k] = __ldg(sv + k);
+        const uint32_t done = nvec << 4;
+        if (lane < (n & 15u)) dst[done + lane] = src[done + lane];
+        return;
+    }
+    // dst = 16-byte aligned base + mis: build each aligned 16-byte store from two consecutive source vectors
+    const uint32_t head = 16u - mis;  // bytes until dst is aligned
+    if (n <= head + 16) {
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = src[k];
+        return;
+    }
+    if (lane < head) dst[lane] = src[lane];
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t rem = n - head, nvec = rem >> 4;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);  // src + head = word (head>>2), byte shift (head&3)
+    const uint32_t wsh = head >> 2, bsh = (head & 3u) * 8u;
+    for (uint32_t k = lane; k < nvec; k += 32) {
+        const uint32_t *q = sw + wsh + 4 * (size_t)k;
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
+        const uint32_t w4 = bsh ? __ldg(q + 4) : 0u;
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, bsh);
+        o.y = __funnelshift_r(w1, w2, bsh);
+        o.z = __funnelshift_r(w2, w3, bsh);
+        o.w = __funnelshift_r(w3, w4, bsh);
+        dv[k] = o;
+    }
+    const uint32_t done = head + (nvec << 4);
+    if (lane < (rem & 15u)) dst[done + lane] = src[done + lane];
+}
+
+// Ask L2 to fetch [p, p+bytes) (bytes multiple of 16, p 16-byte aligned); one thread issues it.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- XXH32 of the frame descriptor (2 or 10 bytes), for the header checksum byte -----------------
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
 __device__ __forceinline__ uint32_t xxh32_small(const uint8_t *p, uint32_t len) {  // len < 16, seed 0
@@ -192,17 +241,19 @@ __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict
                 h = lz4_hash(v);
                 cand = ht[h];
             }
-            __syncwarp();
-            if (valid) ht[h] = (uint16_t)pos;
-            __syncwarp();
             const bool hit = valid && cand < pos && load32(src, cand) == v;
-            const unsigned hits = __ballot_sync(kFull, hit);
+            const unsigned hits = __ballot_sync(kFull, hit);  // (also orders the table reads before the writes)
+            // Only positions up to the winning lane enter the table: later lanes lie inside / after the
+            // coming match, and inserting them would replace useful older candidates with positions the
+            // cursor has not reached yet (which the cand < pos test then rejects as self-references).
+            const int m = hits ? __ffs(hits) - 1 : 31;
+            if (valid && (int)lane <= m) ht[h] = (uint16_t)pos;
+            __syncwarp();
             if (hits == 0) {
                 ip += 32 * step;
                 nprobe += 32;
                 continue;
             }
-            const int m = __ffs(hits) - 1;
             uint32_t mpos = __shfl_sync(kFull, pos, m);
             uint32_t mcand = __shfl_sync(kFull, cand, m);
 

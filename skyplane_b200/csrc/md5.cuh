@@ -128,8 +128,10 @@ __device__ __forceinline__ void cp_async_wait() {
 // Digest of one chunk per lane.  `ring` = this warp's 8 KiB shared-memory area (2048 x uint32),
 // `src` 16-byte aligned (or len == 0), `active` false for lanes without a chunk.
 // Writes 16 digest bytes to `out` for active lanes.
+// `progress` (may be null): lane 0 publishes how many 64 KiB rows the warp has consumed, so LZ4 warps can
+// fetch a row just ahead of the MD5 lanes and the lanes then hit L2 instead of HBM.
 __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uint64_t len, bool active, uint8_t *out,
-                                         unsigned lane) {
+                                         unsigned lane, volatile uint32_t *progress) {
     constexpr int kSlots = 4;  // ring depth (blocks); prefetch distance = kSlots - 1
     const uint64_t nfull = active ? (len >> 6) : 0;
     uint64_t wmax = nfull;
@@ -152,28 +154,37 @@ __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uin
         }
         cp_async_commit();
     }
+    auto load_words = [&](uint32_t (&w)[16], int cs) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(ring + ((cs * 4 + q) * 32 + lane) * 4);
+            w[4 * q + 0] = v.x;
+            w[4 * q + 1] = v.y;
+            w[4 * q + 2] = v.z;
+            w[4 * q + 3] = v.w;
+        }
+    };
+    // software pipeline: the words of block i+1 are pulled from the ring (LDS) while block i's chain runs
+    uint32_t wn[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) wn[k] = 0;
+    cp_async_wait<kSlots - 2>();  // block 0 has landed
+    if (nfull) load_words(wn, 0);
     for (uint64_t i = 0; i < wmax; i++) {
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = wn[k];
         const uint64_t pf = i + (kSlots - 1);
-        const int ps = (int)(pf & (kSlots - 1));
         if (pf < nfull) {
+            const int ps = (int)(pf & (kSlots - 1));  // == slot of block i-1, last read one iteration ago
 #pragma unroll
             for (int q = 0; q < 4; q++) cp_async16(slot_addr(ps, q), src + pf * 64 + q * 16);
         }
         cp_async_commit();
-        cp_async_wait<kSlots - 1>();
-        if (i < nfull) {
-            const int cs = (int)(i & (kSlots - 1));
-            uint32_t w[16];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(ring + ((cs * 4 + q) * 32 + lane) * 4);
-                w[4 * q + 0] = v.x;
-                w[4 * q + 1] = v.y;
-                w[4 * q + 2] = v.z;
-                w[4 * q + 3] = v.w;
-            }
-            md5_block(st, w);
-        }
+        cp_async_wait<kSlots - 2>();  // block i+1 has landed
+        if (i + 1 < nfull) load_words(wn, (int)((i + 1) & (kSlots - 1)));
+        if (i < nfull) md5_block(st, w);
+        if (progress && lane == 0 && ((i + 1) & 1023) == 0) *progress = (uint32_t)((i + 1) >> 10) + 1u;  // 1 + 64 KiB rows done
     }
     cp_async_wait<0>();
     if (active) {

@@ -7,11 +7,18 @@
 //   * LZ4 warps  : one 64 KiB block per work item (lz4.cuh), claimed from a global atomic counter in
 //                  row-major order (block row j of every chunk, then row j+1 ...).
 // Output placement (single pass, no compaction kernel): block j is compressed into its WORST-CASE
-// slot (15 + j*65540) inside the chunk's output region; when the predecessor publishes where block
-// j really starts (per-chunk chain word, release/acquire), the warp writes the 4-byte block header and,
-// only if the start moved, slides its bytes left (forward move) or -- for a stored block -- copies the
-// input straight to the final place.  Incompressible data therefore costs exactly one read of the input
-// and one write of the output.  The last block's warp writes the EndMark and the frame length.
+// slot (15 + j*65540) inside the chunk's output region.  Two per-chunk words then order the blocks:
+//   OFF  = (next block index, frame offset of that block): a prefix sum handed from block j-1 to block j
+//          as soon as j-1 knows its own size -- before any data is moved, so offsets race down the chain;
+//   FREE = number of leading blocks whose slots no longer hold unmoved bytes.
+// Block j waits for OFF (its final position), publishes OFF for j+1, waits for FREE >= j (nobody before it
+// still needs bytes that its destination may overlap), then: compressed + moved -> slides its bytes left
+// (forward move) and sets FREE = j+1; stored raw (or not moved) -> sets FREE = j+1 at once and copies the
+// input straight to the final place off the chain.  Incompressible data therefore costs exactly one read
+// of the input and one write of the output.  The last block's warp writes the EndMark and the frame length.
+//
+// HBM-read sharing: when MD5 is the slower stage, LZ4 work for block row j is released only when the MD5
+// lanes are within one row of it (per-group progress word), so the lanes find the row in L2.
 //
 // Host side: sky_ctx owns a stream, pinned + device metadata arrays, and (optionally) per-slot input /
 // output slabs for the host-buffer path (H2D -> kernel -> D2H on one stream per slot).
@@ -46,13 +53,15 @@ struct ChunkDesc {
     uint8_t *dst;        // 16-byte aligned
     uint64_t len;
     uint32_t nblk;
-    uint32_t pad;
+    uint32_t group;  // MD5 group (warp) that digests this chunk
 };
 
 struct Params {
     const ChunkDesc *chunks;
     const uint32_t *md5_order;  // chunk indices, longest first, padded with 0xffffffff to 32*n_groups
-    uint64_t *chain;            // per chunk: (next block index << 40) | frame offset of that block
+    uint64_t *chain;            // per chunk OFF word: (next block index << 40) | frame offset of that block
+    uint32_t *freed;            // per chunk FREE word: leading blocks whose slots are free
+    uint32_t *md5_progress;     // per MD5 group: 0 = not started, else 1 + 64 KiB rows consumed (0xffffffff = done)
     uint64_t *out_len;          // per chunk frame length
     uint8_t *md5_out;           // 16 bytes per chunk
     uint32_t *counters;         // [0] = LZ4 work counter
@@ -67,12 +76,25 @@ __device__ __forceinline__ uint64_t ld_acquire(const uint64_t *p) {
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t ld_acquire32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(uint64_t *p, uint64_t v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_release32(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // One LZ4 work item: block j of chunk c.
-__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint16_t *ht, unsigned lane) {
+__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint16_t *ht, unsigned lane, bool pace) {
     const ChunkDesc cd = p.chunks[c];
     if (cd.nblk == 0) {
         if (j == 0 && lane == 0) {  // empty chunk: 7-byte header + EndMark
@@ -83,21 +105,36 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
         return;
     }
     if (j >= cd.nblk) return;
-    if (j == 0 && lane == 0) write_frame_header(cd.dst, cd.len);
 
     const uint64_t boff = (uint64_t)j * kBlock;
     const uint32_t L = (uint32_t)min((uint64_t)kBlock, cd.len - boff);
     const uint8_t *src = cd.src + boff;
+    if (lane == 0) {
+        if (pace) {
+            // stay at most one 64 KiB row ahead of the MD5 lanes of this chunk (only while they are running)
+            const uint32_t *pw = p.md5_progress + cd.group;
+            unsigned ns = 64;
+            for (;;) {
+                const uint32_t pr = ld_relaxed32(pw);
+                if (pr == 0 || j + 1 <= pr) break;  // pr - 1 rows consumed: rows <= pr allowed
+                __nanosleep(ns);
+                if (ns < 4096) ns <<= 1;
+            }
+        }
+        l2_prefetch_bulk(src, (L + 15u) & ~15u);
+        if (j == 0) write_frame_header(cd.dst, cd.len);
+    }
+    __syncwarp();
+
     const uint64_t slot = 15 + (uint64_t)j * kSlot;  // worst-case position of this block's header
     uint8_t *out = cd.dst + slot + 4;
-
     const uint32_t csize = lz4_compress_block(src, L, out, ht, lane);
     __syncwarp();
 
-    // wait for the predecessor to publish where this block starts
+    // OFF chain: learn where this block starts, tell the successor at once
     uint64_t st = 0;
     if (lane == 0) {
-        const uint64_t *cw = p.chain + c;
+        uint64_t *cw = p.chain + c;
         unsigned ns = 32;
         while (((st = ld_acquire(cw)) >> kOffBits) != j) {
             __nanosleep(ns);
@@ -106,27 +143,40 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
     }
     st = __shfl_sync(kFull, st, 0);
     const uint64_t off = st & kOffMask;  // <= slot
-    uint8_t *hdr = cd.dst + off;
-    uint32_t bsize, hword;
-    if (csize) {
-        bsize = csize;
-        hword = csize;
-        if (off != slot) warp_copy(hdr + 4, out, csize, lane);  // slide left (dst < src)
-    } else {
-        bsize = L;
-        hword = L | 0x80000000u;
-        warp_copy(hdr + 4, src, L, lane);  // stored block: straight from the input
-    }
-    if (lane < 4) hdr[lane] = (uint8_t)(hword >> (8 * lane));
+    const uint32_t bsize = csize ? csize : L;
+    const uint32_t hword = csize ? csize : (L | 0x80000000u);
     const uint64_t end = off + 4 + bsize;
-    if (j + 1 == cd.nblk) {
-        if (lane < 4) cd.dst[end + lane] = 0;  // EndMark
-        if (lane == 0) p.out_len[c] = end + 4;
+    const bool last = (j + 1 == cd.nblk);
+    const bool moves = csize != 0 && off != slot;
+    if (lane == 0) {
+        if (!last) st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
+        // FREE chain: every earlier slot must be drained before this block's destination is written
+        uint32_t *fw = p.freed + c;
+        unsigned ns = 32;
+        while (ld_acquire32(fw) < j) {
+            __nanosleep(ns);
+            if (ns < 1024) ns <<= 1;
+        }
+        if (!moves) st_release32(fw, j + 1);  // this slot holds nothing a successor could clobber
     }
     __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
+    uint8_t *hdr = cd.dst + off;
+    if (csize) {
+        if (moves) {
+            warp_copy(hdr + 4, out, csize, lane);  // slide left (dst < src, forward move)
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                st_release32(p.freed + c, j + 1);
+            }
+        }
+    } else {
+        warp_copy_input(hdr + 4, src, L, lane);  // stored block: straight from the input
+    }
+    if (lane < 4) hdr[lane] = (uint8_t)(hword >> (8 * lane));
+    if (last) {
+        if (lane < 4) cd.dst[end + lane] = 0;  // EndMark
+        if (lane == 0) p.out_len[c] = end + 4;
     }
 }
 
@@ -148,7 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) 
                 src = p.chunks[c].src;
                 len = p.chunks[c].len;
             }
-            md5_warp(reinterpret_cast<uint32_t *>(my), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16, lane);
+            volatile uint32_t *prog = p.md5_progress + g;
+            if (lane == 0) *prog = 1u;  // started, 0 rows consumed
+            md5_warp(reinterpret_cast<uint32_t *>(my), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16, lane, prog);
+            if (lane == 0) *prog = 0xffffffffu;
             __syncwarp();
         }
     }
@@ -159,13 +212,14 @@ __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) 
         const unsigned sub = warp & 3;
         if (sub * gridDim.x + blockIdx.x < p.n_groups) return;
     }
+    const bool pace = do_md5 && !(p.flags & SKY_F_NO_PACING);
     const uint32_t total = p.rows * p.n_chunks;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(p.counters, 1u);
         w = __shfl_sync(kFull, w, 0);
         if (w >= total) break;
-        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint16_t *>(my), lane);
+        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint16_t *>(my), lane, pace);
         __syncwarp();
     }
 }
@@ -183,6 +237,7 @@ struct Slot {
     ChunkDesc *h_desc = nullptr, *d_desc = nullptr;
     uint32_t *h_order = nullptr, *d_order = nullptr;
     uint64_t *h_chain = nullptr, *d_chain = nullptr;
+    uint32_t *d_freed = nullptr, *d_progress = nullptr;
     uint64_t *h_outlen = nullptr, *d_outlen = nullptr;
     uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
     uint32_t *d_counters = nullptr;
@@ -272,6 +327,8 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_outlen, nc * sizeof(uint64_t)));
     CK(ctx, cudaMalloc(&s.d_md5, nc * 16));
     CK(ctx, cudaMalloc(&s.d_counters, 64));
+    CK(ctx, cudaMalloc(&s.d_freed, nc * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&s.d_progress, (ng / 32 + 1) * sizeof(uint32_t)));
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(ctx, cudaEventCreate(&s.ev_k0));
     CK(ctx, cudaEventCreate(&s.ev_k1));
@@ -281,7 +338,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
 static void free_slot(Slot &s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
-    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_outlen); cudaFree(s.d_md5); cudaFree(s.d_counters);
+    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_outlen); cudaFree(s.d_md5); cudaFree(s.d_counters); cudaFree(s.d_freed); cudaFree(s.d_progress);
     cudaFree(s.d_in); cudaFree(s.d_out);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -370,7 +427,7 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
         const uint64_t nb = (src_len[i] + kBlock - 1) / kBlock;
         if (nb >= (1ull << 24)) return SKY_E_CAPACITY;
         d.nblk = (uint32_t)nb;
-        d.pad = 0;
+        d.group = 0;
         rows = std::max(rows, d.nblk);
         s.h_chain[i] = 15;  // block 0 starts right after the 15-byte frame header
     }
@@ -380,11 +437,14 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
     std::iota(s.h_order, s.h_order + n, 0u);
     std::stable_sort(s.h_order, s.h_order + n, [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
     for (uint32_t i = n; i < ng * 32; i++) s.h_order[i] = 0xffffffffu;
+    for (uint32_t i = 0; i < n; i++) s.h_desc[s.h_order[i]].group = i / 32;
 
     CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemcpyAsync(s.d_order, s.h_order, ng * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemcpyAsync(s.d_chain, s.h_chain, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
+    CK(ctx, cudaMemsetAsync(s.d_freed, 0, n * sizeof(uint32_t), st));
+    CK(ctx, cudaMemsetAsync(s.d_progress, 0, (ng + 1) * sizeof(uint32_t), st));
     CK(ctx, cudaMemsetAsync(s.d_outlen, 0, n * sizeof(uint64_t), st));
     CK(ctx, cudaMemsetAsync(s.d_md5, 0, n * 16, st));
 
@@ -392,6 +452,8 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
     p.chunks = s.d_desc;
     p.md5_order = s.d_order;
     p.chain = s.d_chain;
+    p.freed = s.d_freed;
+    p.md5_progress = s.d_progress;
     p.out_len = s.d_outlen;
     p.md5_out = s.d_md5;
     p.counters = s.d_counters;

@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "libskychunk.so"
 
 SKY_OK = 0
 SKY_E_INVALID, SKY_E_NOGPU, SKY_E_CUDA, SKY_E_CAPACITY, SKY_E_BUSY, SKY_E_TICKET, SKY_E_NOMEM = -1, -2, -3, -4, -5, -6, -7
-F_LZ4, F_MD5, F_MD5_EXCLUSIVE = 1, 2, 4
+F_LZ4, F_MD5, F_MD5_EXCLUSIVE, F_NO_PACING = 1, 2, 4, 8
 
 # every symbol include/skychunk.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = (

@@ -45,7 +45,8 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
-    FL = {"lz4": native.F_LZ4, "md5": native.F_MD5, "both": 0, "both_excl": native.F_MD5_EXCLUSIVE, "md5_excl": native.F_MD5 | native.F_MD5_EXCLUSIVE}
+    FL = {"lz4": native.F_LZ4, "md5": native.F_MD5, "both": 0, "both_excl": native.F_MD5_EXCLUSIVE, "md5_excl": native.F_MD5 | native.F_MD5_EXCLUSIVE,
+          "both_nopace": native.F_NO_PACING}
     for wl in a.workloads.split(","):
         for sz in a.sizes_mib.split(","):
             chunk_bytes = int(float(sz) * (1 << 20))
