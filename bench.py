@@ -344,43 +344,56 @@ def run_gpu(args):
                 pin_in.view[i * stride_in : i * stride_in + chunk_bytes] = synth.silesia_like_chunk(2000 + i + 64 * rank, chunk_bytes)
         pin_out = [native.PinnedBuffer(sub * stride_out) for _ in range(slots)]
 
-        def e2e_step():
-            """All n_chunks chunks through submit/wait, `slots` sub-batches in flight."""
-            inflight = []
-            got = 0
-            h2d = d2h = 0
-            for b in range(n_sub):
-                lo, hi = b * sub, min(n_chunks, (b + 1) * sub)
-                if len(inflight) == slots:
-                    t, ob = inflight.pop(0)
-                    ol, dg, _ = ectx.wait(t)
-                    d2h += sum(ol) + 24 * len(ol)
-                    got += len(ol)
-                ob = pin_out[b % slots]
-                src = [pin_in.addr + ((i % pool_n) * stride_in) for i in range(lo, hi)]
-                dst = [ob.addr + (i - lo) * stride_out for i in range(lo, hi)]
-                t = ectx.submit(src, [chunk_bytes] * (hi - lo), dst, [bound] * (hi - lo))
-                h2d += (hi - lo) * chunk_bytes
-                inflight.append((t, ob))
-            while inflight:
-                t, ob = inflight.pop(0)
-                ol, dg, _ = ectx.wait(t)
-                d2h += sum(ol) + 24 * len(ol)
-                got += len(ol)
-            assert got == n_chunks
-            return h2d, d2h, dg
+        class Pipe:
+            """Continuous sky_submit / sky_wait pipeline: `slots` sub-batches in flight, across step boundaries."""
 
+            def __init__(self):
+                self.inflight = []
+                self.h2d = self.d2h = self.done = 0
+                self.last_dg = None
+                self.b = 0
+
+            def push_step(self):
+                for b in range(n_sub):
+                    lo, hi = b * sub, min(n_chunks, (b + 1) * sub)
+                    if len(self.inflight) == slots:
+                        self.pop()
+                    ob = pin_out[self.b % slots]
+                    self.b += 1
+                    src = [pin_in.addr + ((i % pool_n) * stride_in) for i in range(lo, hi)]
+                    dst = [ob.addr + (i - lo) * stride_out for i in range(lo, hi)]
+                    t = ectx.submit(src, [chunk_bytes] * (hi - lo), dst, [bound] * (hi - lo))
+                    self.h2d += (hi - lo) * chunk_bytes
+                    self.inflight.append(t)
+
+            def pop(self):
+                ol, dg, _ = ectx.wait(self.inflight.pop(0))
+                self.d2h += sum(ol) + 24 * len(ol)
+                self.done += len(ol)
+                self.last_dg = dg
+
+            def drain(self):
+                while self.inflight:
+                    self.pop()
+
+        pipe = Pipe()
         for _ in range(max(1, min(2, args.warmup))):
-            h2d, d2h, dg = e2e_step()
+            pipe.push_step()
+        pipe.drain()
+        dg = pipe.last_dg
         if dg[-1] != hashlib.md5(bytes(pin_in.view[((n_chunks - 1) % pool_n) * stride_in : ((n_chunks - 1) % pool_n) * stride_in + chunk_bytes])).digest():
             raise SystemExit("e2e MD5 mismatch against hashlib")
         barrier()
         el0 = ectx.launches
+        pipe = Pipe()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            h2d, d2h, dg = e2e_step()
+            pipe.push_step()
+        pipe.drain()  # every frame of all K steps is back in host memory
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        assert pipe.done == n_chunks * args.steps
+        h2d, d2h = pipe.h2d // args.steps, pipe.d2h // args.steps
         barrier()
         dt = max_over_ranks(dt, dev)
         e2e = {"value": world * total_in * args.steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

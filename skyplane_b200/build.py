@@ -35,6 +35,18 @@ def needs_build() -> bool:
     return any(d.stat().st_mtime > t for d in DEPS)
 
 
+def build_variant(out: Path, defines: dict, verbose: bool = False) -> Path:
+    """Tuning builds for tools/ (same ABI, different kernel constants), e.g. {"SKY_WARPS": 24, "SKY_HASHLOG": 11}."""
+    cmd = [nvcc_path(), *NVCC_FLAGS, *[f"-D{k}={v}" for k, v in defines.items()], *(["-Xptxas", "-v"] if verbose else []),
+           "-o", str(out), *map(str, SOURCES)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(r.stderr, file=sys.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB

@@ -17,7 +17,10 @@ namespace sky {
 
 constexpr uint32_t kBlock = 65536;       // BD = 0x40
 constexpr uint32_t kSlot = kBlock + 4;   // worst-case block footprint in the frame (header + raw data)
-constexpr uint32_t kHashLog = 12;
+#ifndef SKY_HASHLOG
+#define SKY_HASHLOG 12
+#endif
+constexpr uint32_t kHashLog = SKY_HASHLOG;
 constexpr uint32_t kHashSize = 1u << kHashLog;
 constexpr uint32_t kMinMatch = 4;
 constexpr uint32_t kMfLimit = 12;        // a match must start >= 12 bytes before the block end
@@ -92,9 +95,9 @@ __device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__r
         uint32_t k = lane;
         for (; k + 96 < nvec; k += 128) {
             const uint4 a = __ldg(sv + k), b = __ldg(sv + k + 32), c = __ldg(sv + k + 64), d = __ldg(sv + k + 96);
-            dv[k] = a; dv[k + 32] = b; dv[k + 64] = c; dv[k + 96] = d;
+            __stcs(dv + k, a); __stcs(dv + k + 32, b); __stcs(dv + k + 64, c); __stcs(dv + k + 96, d);
         }
-        for (; k < nvec; k += 32) dv[k] = __ldg(sv + k);
+        for (; k < nvec; k += 32) __stcs(dv + k, __ldg(sv + k));
         const uint32_t done = nvec << 4;
         if (lane < (n & 15u)) dst[done + lane] = src[done + lane];
         return;
@@ -119,7 +122,7 @@ __device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__r
         o.y = __funnelshift_r(w1, w2, bsh);
         o.z = __funnelshift_r(w2, w3, bsh);
         o.w = __funnelshift_r(w3, w4, bsh);
-        dv[k] = o;
+        __stcs(dv + k, o);  // streaming: the frame is never re-read here, keep L2 for the input rows
     }
     const uint32_t done = head + (nvec << 4);
     if (lane < (rem & 15u)) dst[done + lane] = src[done + lane];

@@ -41,10 +41,17 @@
 
 namespace sky {
 
-constexpr int kWarps = 16;
+#ifndef SKY_WARPS
+#define SKY_WARPS 16
+#endif
+constexpr int kWarps = SKY_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMd5WarpsPerCta = 4;  // warps 0..3 (one per SM sub-partition) may host MD5 groups
-constexpr uint32_t kSmemBytes = kWarps * kHashSize * 2;  // 128 KiB: one 8 KiB table / MD5 ring per warp
+constexpr uint32_t kTableBytes = kHashSize * 2;  // LZ4 match table: u16 positions
+constexpr uint32_t kRingBytes = 8192;           // MD5 staging ring: 4 slots x 64 B x 32 lanes
+constexpr uint32_t kMd5AreaBytes = kTableBytes > kRingBytes ? kTableBytes : kRingBytes;
+// warps 0..3 (MD5-capable) own kMd5AreaBytes each, the others one match table each (16 x 8 KiB = 128 KiB by default)
+constexpr uint32_t kSmemBytes = kMd5WarpsPerCta * kMd5AreaBytes + (kWarps - kMd5WarpsPerCta) * kTableBytes;
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
 
@@ -183,7 +190,8 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
 __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *my = smem + warp * (kHashSize * 2);
+    uint8_t *my = warp < kMd5WarpsPerCta ? smem + warp * kMd5AreaBytes
+                                         : smem + kMd5WarpsPerCta * kMd5AreaBytes + (warp - kMd5WarpsPerCta) * kTableBytes;
 
     const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
     const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
@@ -232,7 +240,8 @@ using namespace sky;
 struct Slot {
     cudaStream_t stream = nullptr;
     uint8_t *d_in = nullptr, *d_out = nullptr;
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_res = nullptr;  // kernel start / end, results (sizes+digests) on host
+    bool d2h_issued = false;
     // per-batch metadata (device + pinned host mirrors)
     ChunkDesc *h_desc = nullptr, *d_desc = nullptr;
     uint32_t *h_order = nullptr, *d_order = nullptr;
@@ -332,6 +341,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(ctx, cudaEventCreate(&s.ev_k0));
     CK(ctx, cudaEventCreate(&s.ev_k1));
+    CK(ctx, cudaEventCreateWithFlags(&s.ev_res, cudaEventDisableTiming));
     return SKY_OK;
 }
 
@@ -342,6 +352,7 @@ static void free_slot(Slot &s) {
     cudaFree(s.d_in); cudaFree(s.d_out);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_res) cudaEventDestroy(s.ev_res);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -468,6 +479,28 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
     ctx->launches++;
     CK(ctx, cudaMemcpyAsync(s.h_outlen, s.d_outlen, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CK(ctx, cudaMemcpyAsync(s.h_md5, s.d_md5, n * 16, cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaEventRecord(s.ev_res, st));
+    return SKY_OK;
+}
+
+// Frame copies need the compressed sizes, which only exist after the kernel.  Every host-path entry point
+// calls this: for each in-flight slot whose sizes have reached the host (ev_res done) it enqueues the exact-length
+// D2H copies on that slot's stream, so batch k's D2H overlaps batch k+1's H2D and kernel without a helper thread.
+static int issue_d2h(sky_ctx *ctx, Slot &s) {
+    for (uint32_t i = 0; i < s.n; i++)
+        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, s.stream));
+    s.d2h_issued = true;
+    return SKY_OK;
+}
+static int progress(sky_ctx *ctx) {
+    for (auto &s : ctx->slots) {
+        if (!s.busy || s.d2h_issued) continue;
+        cudaError_t q = cudaEventQuery(s.ev_res);
+        if (q == cudaErrorNotReady) continue;
+        CK(ctx, q);
+        int rc = issue_d2h(ctx, s);
+        if (rc != SKY_OK) return rc;
+    }
     return SKY_OK;
 }
 
@@ -505,6 +538,7 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
     if (!sp) return ctx->slots[0].d_in ? SKY_E_BUSY : SKY_E_INVALID;
     Slot &s = *sp;
     CK(ctx, cudaSetDevice(ctx->device));
+    { int prc = progress(ctx); if (prc != SKY_OK) return prc; }
     std::vector<uint64_t> in_off(n), out_off(n);
     uint64_t ip = 0, op = 0;
     for (uint32_t i = 0; i < n; i++) {
@@ -521,6 +555,7 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
     int rc = launch_batch(ctx, s, s.stream, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), 0);
     if (rc != SKY_OK) return rc;
     s.busy = true;
+    s.d2h_issued = false;
     s.ticket = ctx->next_ticket++;
     s.n = n;
     s.dst.assign(dst, dst + n);
@@ -537,9 +572,13 @@ int sky_wait(sky_ctx *ctx, uint64_t ticket, uint64_t *out_len, uint8_t *md5, flo
     if (!sp) return SKY_E_TICKET;
     Slot &s = *sp;
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaStreamSynchronize(s.stream));  // sizes + digests are on the host now
-    for (uint32_t i = 0; i < s.n; i++)
-        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, s.stream));
+    { int prc = progress(ctx); if (prc != SKY_OK) return prc; }
+    if (!s.d2h_issued) {
+        CK(ctx, cudaEventSynchronize(s.ev_res));  // sizes + digests are on the host now
+        int rc = issue_d2h(ctx, s);
+        if (rc != SKY_OK) return rc;
+    }
+    { int prc = progress(ctx); if (prc != SKY_OK) return prc; }  // let later batches' copies queue up behind ours
     CK(ctx, cudaStreamSynchronize(s.stream));
     if (out_len) memcpy(out_len, s.h_outlen, s.n * sizeof(uint64_t));
     if (md5) memcpy(md5, s.h_md5, (size_t)s.n * 16);

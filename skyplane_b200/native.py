@@ -49,11 +49,17 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    import os
+
     from skyplane_b200 import build as _build
 
-    if _build.needs_build():
-        _build.build()
-    L = ctypes.CDLL(str(LIB_PATH))
+    override = os.environ.get("SKYCHUNK_LIB")  # tuning builds (tools/): same ABI, different kernel constants
+    if override:
+        L = ctypes.CDLL(override)
+    else:
+        if _build.needs_build():
+            _build.build()
+        L = ctypes.CDLL(str(LIB_PATH))
     vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
     p_u64 = ctypes.POINTER(u64)
     L.sky_strerror.argtypes = [i32]
