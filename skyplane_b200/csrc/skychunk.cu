@@ -552,7 +552,10 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
     if (ip > ctx->in_cap || op > ctx->out_cap) return SKY_E_CAPACITY;
     for (uint32_t i = 0; i < n; i++)
         if (src_len[i]) CK(ctx, cudaMemcpyAsync(s.d_in + in_off[i], src[i], src_len[i], cudaMemcpyHostToDevice, s.stream));
-    int rc = launch_batch(ctx, s, s.stream, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), 0);
+    // No MD5 pacing on the host path: paced LZ4 warps keep every CTA resident for the whole MD5 chain (tens of
+    // ms), which would serialise the kernels of different slots; unpaced, a batch's LZ4 CTAs retire in a few ms
+    // and the next slot's kernel overlaps this one's MD5 tail.
+    int rc = launch_batch(ctx, s, s.stream, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), SKY_F_NO_PACING);
     if (rc != SKY_OK) return rc;
     s.busy = true;
     s.d2h_issued = false;
