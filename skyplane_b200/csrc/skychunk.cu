@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -242,13 +243,17 @@ struct Slot {
     uint8_t *d_in = nullptr, *d_out = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_res = nullptr;  // kernel start / end, results (sizes+digests) on host
     bool d2h_issued = false;
+    cudaEvent_t ev_h0 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;  // SKYCHUNK_TRACE only: H2D start, D2H start / end
     // per-batch metadata (device + pinned host mirrors)
     ChunkDesc *h_desc = nullptr, *d_desc = nullptr;
     uint32_t *h_order = nullptr, *d_order = nullptr;
     uint64_t *h_chain = nullptr, *d_chain = nullptr;
     uint32_t *d_freed = nullptr, *d_progress = nullptr;
-    uint64_t *h_outlen = nullptr, *d_outlen = nullptr;
+    // results live in MAPPED pinned host memory: the kernel stores sizes / digests straight over PCIe, so no small
+    // device->host copies sit in a copy-engine queue behind multi-GiB frame copies
+    uint64_t *h_outlen = nullptr, *d_outlen = nullptr;  // same allocation, host / device view
     uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;  // input landed (on ctx->st_h2d) / frames landed (on ctx->st_d2h)
     uint32_t *d_counters = nullptr;
     // in-flight ticket
     bool busy = false;
@@ -268,6 +273,12 @@ struct sky_ctx {
     uint64_t next_ticket = 1;
     uint64_t launches = 0;
     std::string err;
+    // Host path: every slot's input copies go FIFO through one H2D stream and every frame copy through one D2H
+    // stream, so the two directions use different copy engines and batch k's frames leave while batch k+1's
+    // input arrives (per-slot streams put both directions of all slots into one in-order engine queue).
+    cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    bool trace = false;           // SKYCHUNK_TRACE=1: print per-batch device timeline to stderr
+    cudaEvent_t ev_base = nullptr;
 };
 
 static thread_local std::string g_err;
@@ -328,31 +339,41 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMallocHost(&s.h_desc, nc * sizeof(ChunkDesc)));
     CK(ctx, cudaMallocHost(&s.h_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMallocHost(&s.h_chain, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMallocHost(&s.h_outlen, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMallocHost(&s.h_md5, nc * 16));
+    CK(ctx, cudaHostAlloc(&s.h_outlen, nc * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(ctx, cudaHostAlloc(&s.h_md5, nc * 16, cudaHostAllocMapped | cudaHostAllocPortable));
+    CK(ctx, cudaHostGetDevicePointer(&s.d_outlen, s.h_outlen, 0));
+    CK(ctx, cudaHostGetDevicePointer(&s.d_md5, s.h_md5, 0));
+    CK(ctx, cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
     CK(ctx, cudaMalloc(&s.d_desc, nc * sizeof(ChunkDesc)));
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMalloc(&s.d_outlen, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMalloc(&s.d_md5, nc * 16));
     CK(ctx, cudaMalloc(&s.d_counters, 64));
     CK(ctx, cudaMalloc(&s.d_freed, nc * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_progress, (ng / 32 + 1) * sizeof(uint32_t)));
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(ctx, cudaEventCreate(&s.ev_k0));
     CK(ctx, cudaEventCreate(&s.ev_k1));
-    CK(ctx, cudaEventCreateWithFlags(&s.ev_res, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreate(&s.ev_res));
+    CK(ctx, cudaEventCreate(&s.ev_h0));
+    CK(ctx, cudaEventCreate(&s.ev_d0));
+    CK(ctx, cudaEventCreate(&s.ev_d1));
     return SKY_OK;
 }
 
 static void free_slot(Slot &s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
-    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_outlen); cudaFree(s.d_md5); cudaFree(s.d_counters); cudaFree(s.d_freed); cudaFree(s.d_progress);
+    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters); cudaFree(s.d_freed); cudaFree(s.d_progress);
     cudaFree(s.d_in); cudaFree(s.d_out);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_res) cudaEventDestroy(s.ev_res);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
+    if (s.ev_h0) cudaEventDestroy(s.ev_h0);
+    if (s.ev_d0) cudaEventDestroy(s.ev_d0);
+    if (s.ev_d1) cudaEventDestroy(s.ev_d1);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -399,6 +420,16 @@ int sky_ctx_create(int device, uint64_t max_batch_bytes, uint32_t max_chunks, ui
             if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc(slab): ") + cudaGetErrorString(e); return fail(SKY_E_NOMEM); }
         }
     }
+    if (n_slots) {
+        e = cudaStreamCreateWithFlags(&ctx->st_h2d, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->st_d2h, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return fail(SKY_E_CUDA); }
+    }
+    ctx->trace = getenv("SKYCHUNK_TRACE") != nullptr;
+    if (ctx->trace) {
+        cudaEventCreate(&ctx->ev_base);
+        cudaEventRecord(ctx->ev_base, ctx->slots[0].stream);
+    }
     *out = ctx;
     return SKY_OK;
 }
@@ -407,6 +438,9 @@ int sky_ctx_destroy(sky_ctx *ctx) {
     if (!ctx) return SKY_E_INVALID;
     cudaSetDevice(ctx->device);
     for (auto &s : ctx->slots) free_slot(s);
+    if (ctx->st_h2d) { cudaStreamSynchronize(ctx->st_h2d); cudaStreamDestroy(ctx->st_h2d); }
+    if (ctx->st_d2h) { cudaStreamSynchronize(ctx->st_d2h); cudaStreamDestroy(ctx->st_d2h); }
+    if (ctx->ev_base) cudaEventDestroy(ctx->ev_base);
     delete ctx;
     return SKY_OK;
 }
@@ -426,8 +460,10 @@ int sky_pinned_free(void *p) {
 }
 
 // Fills the slot's metadata for a batch and enqueues: meta H2D, counter reset, fused kernel, results D2H.
-static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, const uint8_t *d_src, const uint64_t *src_off,
-                        const uint64_t *src_len, uint8_t *d_dst, const uint64_t *dst_off, uint32_t flags) {
+// `meta_st`: stream the three small metadata copies ride on (the H2D stream on the host path, so they are
+// never queued behind another batch's frame copies); `st`: the stream the kernel runs on.
+static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t meta_st, uint32_t n, const uint8_t *d_src,
+                        const uint64_t *src_off, const uint64_t *src_len, uint8_t *d_dst, const uint64_t *dst_off, uint32_t flags) {
     if ((flags & (SKY_F_LZ4 | SKY_F_MD5)) == 0) flags |= SKY_F_LZ4 | SKY_F_MD5;
     uint32_t rows = 1;
     for (uint32_t i = 0; i < n; i++) {
@@ -450,14 +486,18 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
     for (uint32_t i = n; i < ng * 32; i++) s.h_order[i] = 0xffffffffu;
     for (uint32_t i = 0; i < n; i++) s.h_desc[s.h_order[i]].group = i / 32;
 
-    CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, st));
-    CK(ctx, cudaMemcpyAsync(s.d_order, s.h_order, ng * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(ctx, cudaMemcpyAsync(s.d_chain, s.h_chain, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemcpyAsync(s.d_desc, s.h_desc, n * sizeof(ChunkDesc), cudaMemcpyHostToDevice, meta_st));
+    CK(ctx, cudaMemcpyAsync(s.d_order, s.h_order, ng * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, meta_st));
+    CK(ctx, cudaMemcpyAsync(s.d_chain, s.h_chain, n * sizeof(uint64_t), cudaMemcpyHostToDevice, meta_st));
+    if (meta_st != st) {
+        CK(ctx, cudaEventRecord(s.ev_h2d, meta_st));  // input (enqueued earlier on meta_st) + metadata have landed
+        CK(ctx, cudaStreamWaitEvent(st, s.ev_h2d, 0));
+    }
     CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
     CK(ctx, cudaMemsetAsync(s.d_freed, 0, n * sizeof(uint32_t), st));
     CK(ctx, cudaMemsetAsync(s.d_progress, 0, (ng + 1) * sizeof(uint32_t), st));
-    CK(ctx, cudaMemsetAsync(s.d_outlen, 0, n * sizeof(uint64_t), st));
-    CK(ctx, cudaMemsetAsync(s.d_md5, 0, n * 16, st));
+    memset(s.h_outlen, 0, n * sizeof(uint64_t));  // host-side clear (mapped memory; the slot is idle here)
+    memset(s.h_md5, 0, (size_t)n * 16);
 
     Params p;
     p.chunks = s.d_desc;
@@ -477,18 +517,20 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, cons
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaEventRecord(s.ev_k1, st));
     ctx->launches++;
-    CK(ctx, cudaMemcpyAsync(s.h_outlen, s.d_outlen, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaMemcpyAsync(s.h_md5, s.d_md5, n * 16, cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaEventRecord(s.ev_res, st));
+    CK(ctx, cudaEventRecord(s.ev_res, st));  // kernel done => sizes + digests are in host memory
     return SKY_OK;
 }
 
 // Frame copies need the compressed sizes, which only exist after the kernel.  Every host-path entry point
 // calls this: for each in-flight slot whose sizes have reached the host (ev_res done) it enqueues the exact-length
-// D2H copies on that slot's stream, so batch k's D2H overlaps batch k+1's H2D and kernel without a helper thread.
+// D2H copies on the ctx's D2H stream, so batch k's D2H overlaps batch k+1's H2D and kernel without a helper thread.
 static int issue_d2h(sky_ctx *ctx, Slot &s) {
+    CK(ctx, cudaStreamWaitEvent(ctx->st_d2h, s.ev_res, 0));
+    if (ctx->trace) CK(ctx, cudaEventRecord(s.ev_d0, ctx->st_d2h));
     for (uint32_t i = 0; i < s.n; i++)
-        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, ctx->st_d2h));
+    if (ctx->trace) CK(ctx, cudaEventRecord(s.ev_d1, ctx->st_d2h));
+    CK(ctx, cudaEventRecord(s.ev_d2h, ctx->st_d2h));
     s.d2h_issued = true;
     return SKY_OK;
 }
@@ -519,7 +561,7 @@ int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, const uint64
     Slot &s = ctx->slots[0];
     if (s.busy) return SKY_E_BUSY;
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-    int rc = launch_batch(ctx, s, st, n, (const uint8_t *)d_src, src_off, src_len, (uint8_t *)d_dst, dst_off, flags);
+    int rc = launch_batch(ctx, s, st, st, n, (const uint8_t *)d_src, src_off, src_len, (uint8_t *)d_dst, dst_off, flags);
     if (rc != SKY_OK) return rc;
     CK(ctx, cudaStreamSynchronize(st));
     if (out_len) memcpy(out_len, s.h_outlen, n * sizeof(uint64_t));
@@ -550,12 +592,14 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
         op += round16(sky_frame_bound(src_len[i]));
     }
     if (ip > ctx->in_cap || op > ctx->out_cap) return SKY_E_CAPACITY;
+    if (ctx->trace) CK(ctx, cudaEventRecord(s.ev_h0, ctx->st_h2d));
     for (uint32_t i = 0; i < n; i++)
-        if (src_len[i]) CK(ctx, cudaMemcpyAsync(s.d_in + in_off[i], src[i], src_len[i], cudaMemcpyHostToDevice, s.stream));
+        if (src_len[i]) CK(ctx, cudaMemcpyAsync(s.d_in + in_off[i], src[i], src_len[i], cudaMemcpyHostToDevice, ctx->st_h2d));
+
     // No MD5 pacing on the host path: paced LZ4 warps keep every CTA resident for the whole MD5 chain (tens of
     // ms), which would serialise the kernels of different slots; unpaced, a batch's LZ4 CTAs retire in a few ms
     // and the next slot's kernel overlaps this one's MD5 tail.
-    int rc = launch_batch(ctx, s, s.stream, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), SKY_F_NO_PACING);
+    int rc = launch_batch(ctx, s, s.stream, ctx->st_h2d, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), SKY_F_NO_PACING);
     if (rc != SKY_OK) return rc;
     s.busy = true;
     s.d2h_issued = false;
@@ -582,10 +626,21 @@ int sky_wait(sky_ctx *ctx, uint64_t ticket, uint64_t *out_len, uint8_t *md5, flo
         if (rc != SKY_OK) return rc;
     }
     { int prc = progress(ctx); if (prc != SKY_OK) return prc; }  // let later batches' copies queue up behind ours
-    CK(ctx, cudaStreamSynchronize(s.stream));
+    CK(ctx, cudaEventSynchronize(s.ev_d2h));
     if (out_len) memcpy(out_len, s.h_outlen, s.n * sizeof(uint64_t));
     if (md5) memcpy(md5, s.h_md5, (size_t)s.n * 16);
     if (kernel_ms) CK(ctx, cudaEventElapsedTime(kernel_ms, s.ev_k0, s.ev_k1));
+    if (ctx->trace) {
+        float h0 = 0, k0 = 0, k1 = 0, rs = 0, d0 = 0, d1 = 0;
+        cudaEventElapsedTime(&h0, ctx->ev_base, s.ev_h0);
+        cudaEventElapsedTime(&k0, ctx->ev_base, s.ev_k0);
+        cudaEventElapsedTime(&k1, ctx->ev_base, s.ev_k1);
+        cudaEventElapsedTime(&rs, ctx->ev_base, s.ev_res);
+        cudaEventElapsedTime(&d0, ctx->ev_base, s.ev_d0);
+        cudaEventElapsedTime(&d1, ctx->ev_base, s.ev_d1);
+        fprintf(stderr, "[skychunk trace] ticket %llu: h2d %.1f..%.1f kernel %.1f..%.1f results %.1f d2h %.1f..%.1f ms\n",
+                (unsigned long long)s.ticket, h0, k0, k0, k1, rs, d0, d1);
+    }
     s.busy = false;
     return SKY_OK;
 }
