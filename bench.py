@@ -43,12 +43,17 @@ _POOL = None
 _COMP = None
 
 
-def _cpu_init(pool_chunks, chunk_bytes, use_ref):
+def _cpu_init(pool_chunks, chunk_bytes, use_ref, workload="random"):
     """Runs in each worker process: build the chunk pool once (seeded -> identical in every worker)."""
     global _POOL, _COMP
     import numpy as np
 
-    _POOL = [np.random.default_rng(1000 + i).bytes(chunk_bytes) for i in range(pool_chunks)]
+    if workload == "random":
+        _POOL = [np.random.default_rng(1000 + i).bytes(chunk_bytes) for i in range(pool_chunks)]
+    else:
+        from skyplane_b200 import synth
+
+        _POOL = [synth.silesia_like_chunk(2000 + i, chunk_bytes) for i in range(pool_chunks)]
     if use_ref:
         import oracle.reflib as ref
 
@@ -82,7 +87,7 @@ class CpuReference:
     """All host cores, one chunk per task -- mirrors the reference's process-per-worker model
     (gateway_operator.py:66-70).  Must be constructed before CUDA is initialised (fork)."""
 
-    def __init__(self, chunk_bytes: int, pool_chunks: int = 16):
+    def __init__(self, chunk_bytes: int, pool_chunks: int = 16, workload: str = "random"):
         import multiprocessing as mp
 
         import oracle.reflib as ref
@@ -93,7 +98,8 @@ class CpuReference:
         self.chunk_bytes = chunk_bytes
         self.engine = (f"liblz4 {ref.version()} LZ4F_compressFrame via ctypes (python-lz4 default prefs) + hashlib.md5"
                        if self.use_ref else "oracle/skyoracle.c port (liblz4.so.1 not found) incl. its MD5")
-        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(pool_chunks, chunk_bytes, self.use_ref))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init, initargs=(pool_chunks, chunk_bytes, self.use_ref, workload))
+        self.workload = workload
         self.pool.map(_cpu_task, range(self.cores * 2))  # touch every worker
 
     def run(self, n_chunks: int) -> float:
@@ -180,18 +186,18 @@ def run_reference(args):
     if rank != 0:
         return 0
     chunk_bytes = args.chunk_mib << 20
-    ref = CpuReference(chunk_bytes)
+    ref = CpuReference(chunk_bytes, workload=args.workload)
     n = args.ref_chunks or args.chunks
     for _ in range(args.warmup):
         ref.run(max(ref.cores, n // 8))
     t = [ref.run(n) for _ in range(args.steps)]
     total = sum(t)
     value = n * chunk_bytes * args.steps / total / 1e9
-    sample = f"{n} x {args.chunk_mib} MiB uniform-random chunks per step (pool of 16 distinct, seeds 1000+i), all {ref.cores} cores, {ref.engine}"
+    sample = f"{n} x {args.chunk_mib} MiB {args.workload} chunks per step (pool of 16 distinct, seeded), all {ref.cores} cores, {ref.engine}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
-        "data": "synthetic", "config": {"workload": f"{n} x {args.chunk_mib} MiB uniform-random chunks", "cpu": cpu_model(), "ratio": ref.last_ratio},
+        "data": "synthetic", "config": {"workload": f"{n} x {args.chunk_mib} MiB {args.workload} chunks", "cpu": cpu_model(), "ratio": ref.last_ratio},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -212,12 +218,12 @@ def run_gpu(args):
     # ---- CPU baseline first: it forks, so it must run before CUDA exists in this process (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(chunk_bytes)
+        ref = CpuReference(chunk_bytes, workload=args.workload)
         n_cpu = args.cpu_chunks  # 1024 x 8 MiB at ~13 ms/chunk/core is ~13 s of CPU work
         ref.run(ref.cores * 2)
         dt = min(ref.run(n_cpu) for _ in range(2))
         cpu = {"value": n_cpu * chunk_bytes / dt / 1e9, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
-               "sample": f"{n_cpu} x {args.chunk_mib} MiB uniform-random chunks, best of 2 passes, all {ref.cores} cores ({cpu_model()}), {ref.engine}",
+               "sample": f"{n_cpu} x {args.chunk_mib} MiB {args.workload} chunks, best of 2 passes, all {ref.cores} cores ({cpu_model()}), {ref.engine}",
                "ratio": ref.last_ratio}
         ref.close()
 

@@ -212,14 +212,42 @@ __device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const ui
     return op;
 }
 
+// ---- cooperative forward extension: all lanes compare 4 bytes each per round, starting at match length `mlen`
+__device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src, uint32_t mpos, uint32_t mcand, uint32_t mlen,
+                                                uint32_t maxlen, unsigned lane) {
+    for (;;) {
+        const uint32_t o = mlen + lane * 4;
+        uint32_t cnt = 0;
+        if (o < maxlen) {
+            const uint32_t x = load32(src, mpos + o) ^ load32(src, mcand + o);
+            cnt = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
+            cnt = min(cnt, maxlen - o);
+        }
+        const unsigned fullm = __ballot_sync(kFull, cnt == 4);
+        if (fullm == kFull) {
+            mlen += 128;
+            continue;
+        }
+        const int f = __ffs(~fullm) - 1;
+        return mlen + 4 * f + __shfl_sync(kFull, cnt, f);
+    }
+}
+
+constexpr int kExtRounds = 7;        // per-lane extension: up to 4 + 4*7 = 32 bytes before going cooperative
+constexpr uint32_t kCoopLit = 48;    // literal runs at least this long are copied by the whole warp
+
 // ---- the block compressor -------------------------------------------------------------------------
 // src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: where compressed
-// bytes may be written (capacity L bytes), ht: this warp's 4096-entry table.
+// bytes may be written (capacity L bytes), ht: this warp's match table.
 // Returns the compressed size (1..L-1), or 0 if the block does not shrink (caller stores it raw).
+//
+// One iteration handles a whole window of 32 cursor positions: every lane probes its position, lanes with a
+// verified candidate extend their own match (lane-parallel), then matches are accepted greedily in position
+// order (a match is skipped if it starts inside an accepted one -- exactly what the sequential reference
+// does), and all accepted sequences are sized with a warp scan and written by their own lanes at once.
 __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict__ src, uint32_t L, uint8_t *__restrict__ out,
                                                       uint16_t *ht, unsigned lane) {
-    // clear the table: 8 KiB = 32 lanes x 16 x 16 B
-    {
+    {   // clear the table: 32 lanes x 16 B per round
         uint4 *t4 = reinterpret_cast<uint4 *>(ht);
         const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -229,14 +257,15 @@ __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict
 
     uint32_t ip = 0, anchor = 0, op = 0;
     const uint32_t limit = L - 1;  // accept only csize <= L-1 (LZ4F_makeBlock passes dstCapacity = srcSize-1)
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     if (L >= kMfLimit + 1) {
-        const uint32_t mflimit = L - kMfLimit;        // last position a match may start at
+        const uint32_t mflimit = L - kMfLimit;          // last position a match may start at
         const uint32_t matchlimit = L - kLastLiterals;  // matches end at or before this
         uint32_t nprobe = 1u << kSkipTrigger;           // LZ4: searchMatchNb = acceleration << skipTrigger
         while (ip <= mflimit) {
             const uint32_t step = nprobe >> kSkipTrigger;
-            const uint32_t pos = ip + lane * step;
+            uint32_t pos = ip + lane * step;
             const bool valid = pos <= mflimit;
             uint32_t v = 0, h = 0, cand = 0;
             if (valid) {
@@ -244,67 +273,133 @@ __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict
                 h = lz4_hash(v);
                 cand = ht[h];
             }
-            const bool hit = valid && cand < pos && load32(src, cand) == v;
+            bool hit = valid && cand < pos && load32(src, cand) == v;
+            // The table only knows positions before this window.  A nearer occurrence inside the window (offsets
+            // below 32*step: runs, short periods, repeated words) is found by matching the 4-byte values across
+            // lanes; like the sequential reference, the most recent occurrence wins.
+            {
+                const unsigned vmask = __ballot_sync(kFull, valid);
+                const unsigned same = __match_any_sync(kFull, valid ? v : (0x9e3779b9u ^ lane)) & vmask & lt_mask;
+                if (valid && same) {
+                    cand = ip + (uint32_t)(31 - __clz(same)) * step;
+                    hit = true;
+                }
+            }
             const unsigned hits = __ballot_sync(kFull, hit);  // (also orders the table reads before the writes)
-            // Only positions up to the winning lane enter the table: later lanes lie inside / after the
-            // coming match, and inserting them would replace useful older candidates with positions the
-            // cursor has not reached yet (which the cand < pos test then rejects as self-references).
-            const int m = hits ? __ffs(hits) - 1 : 31;
-            if (valid && (int)lane <= m) ht[h] = (uint16_t)pos;
+            // every probed position enters the table: the cursor always moves past the whole window, so no
+            // entry can point ahead of a later probe
+            if (valid) ht[h] = (uint16_t)pos;
             __syncwarp();
             if (hits == 0) {
                 ip += 32 * step;
                 nprobe += 32;
                 continue;
             }
-            uint32_t mpos = __shfl_sync(kFull, pos, m);
-            uint32_t mcand = __shfl_sync(kFull, cand, m);
-
-            // backward extension ("catch up")
-            {
-                uint32_t room = min(mpos - anchor, mcand);
-                while (room) {
-                    const bool eq = lane < room && src[mpos - 1 - lane] == src[mcand - 1 - lane];
-                    const unsigned em = __ballot_sync(kFull, eq);
-                    const uint32_t nb = (em == kFull) ? 32u : (uint32_t)(__ffs(~em) - 1);
-                    mpos -= nb;
-                    mcand -= nb;
-                    room -= nb;
-                    if (nb < 32) break;
+            // ---- lane-parallel forward extension (bounded); `more` = still matching at the bound
+            uint32_t mlen = 0;
+            bool more = false;
+            if (hit) {
+                const uint32_t maxlen = matchlimit - pos;  // >= 7
+                mlen = kMinMatch;
+                more = true;
+#pragma unroll 1
+                for (int r = 0; r < kExtRounds && mlen < maxlen; r++) {
+                    const uint32_t x = load32(src, pos + mlen) ^ load32(src, cand + mlen);
+                    if (x) {
+                        mlen += (uint32_t)(__ffs(x) - 1) >> 3;
+                        more = false;
+                        break;
+                    }
+                    mlen += 4;
+                }
+                if (mlen >= maxlen) {
+                    mlen = maxlen;
+                    more = false;
                 }
             }
-            // forward extension, 4 bytes per lane per round
-            uint32_t mlen = kMinMatch;
-            {
-                const uint32_t maxlen = matchlimit - mpos;  // >= 7
-                for (;;) {
-                    const uint32_t o = mlen + lane * 4;
-                    uint32_t cnt = 0;
-                    if (o < maxlen) {
-                        const uint32_t x = load32(src, mpos + o) ^ load32(src, mcand + o);
-                        cnt = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
-                        cnt = min(cnt, maxlen - o);
-                    }
-                    const unsigned fullm = __ballot_sync(kFull, cnt == 4);
-                    if (fullm == kFull) {
-                        mlen += 128;
-                        continue;
-                    }
-                    const int f = __ffs(~fullm) - 1;
-                    mlen += 4 * f + __shfl_sync(kFull, cnt, f);
-                    break;
-                }
-            }
-            const uint32_t ll = mpos - anchor;
-            const uint32_t need = seq_bytes(ll, mlen);
-            if (op + need + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
-            op = emit_seq(out, op, src, anchor, ll, mlen, mpos - mcand, lane);
-            ip = mpos + mlen;
-            anchor = ip;
-            nprobe = 1u << kSkipTrigger;
-            // like LZ4_putPosition(ip-2): remember a position inside the match tail
-            if (lane == 0 && ip <= mflimit + 2 && ip >= 2) ht[lz4_hash(load32(src, ip - 2))] = (uint16_t)(ip - 2);
             __syncwarp();
+            // ---- greedy acceptance in position order
+            unsigned sel = 0, rem = hits;
+            while (rem) {
+                const int l = __ffs(rem) - 1;
+                const uint32_t p_l = ip + (uint32_t)l * step;
+                uint32_t len_l = __shfl_sync(kFull, mlen, l);
+                if (__shfl_sync(kFull, (int)more, l)) {  // long match: finish it with the whole warp
+                    len_l = extend_coop(src, p_l, __shfl_sync(kFull, cand, l), len_l, matchlimit - p_l, lane);
+                    if ((int)lane == l) mlen = len_l;
+                }
+                sel |= 1u << l;
+                rem &= __ballot_sync(kFull, pos >= p_l + len_l);  // drop every hit that starts inside this match
+            }
+            const bool is_sel = (sel >> lane) & 1u;
+            const unsigned before = sel & lt_mask;
+            const int prev_l = before ? 31 - __clz(before) : -1;
+            const uint32_t e_mine = pos + mlen;
+            uint32_t prev_end = __shfl_sync(kFull, e_mine, prev_l < 0 ? 0 : prev_l);
+            if (prev_l < 0) prev_end = anchor;
+            // ---- backward extension ("catch up"); only probes that skipped positions can gain from it
+            if (step > 1 && is_sel) {
+                const uint32_t room = min(pos - prev_end, cand);
+                uint32_t b = 0;
+                while (b < room && src[pos - 1 - b] == src[cand - 1 - b]) b++;
+                pos -= b;
+                cand -= b;
+                mlen += b;
+            }
+            const uint32_t ll = is_sel ? pos - prev_end : 0;
+            const uint32_t sz = is_sel ? seq_bytes(ll, mlen) : 0;
+            uint32_t incl = sz;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            if (op + total + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
+            uint32_t lit_o = 0;
+            if (is_sel) {
+                uint32_t o = op + incl - sz;
+                const uint32_t mcode = mlen - kMinMatch;
+                out[o++] = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mcode < 15 ? mcode : 15));
+                if (ll >= 15) {
+                    uint32_t r = ll - 15;
+                    for (; r >= 255; r -= 255) out[o++] = 255;
+                    out[o++] = (uint8_t)r;
+                }
+                lit_o = o;
+                if (ll < kCoopLit) {
+                    uint32_t k = 0;
+                    for (; k + 4 <= ll; k += 4) {  // 4 literal bytes per round: one unaligned read, four byte stores
+                        const uint32_t w = load32(src, prev_end + k);
+                        out[o + k] = (uint8_t)w;
+                        out[o + k + 1] = (uint8_t)(w >> 8);
+                        out[o + k + 2] = (uint8_t)(w >> 16);
+                        out[o + k + 3] = (uint8_t)(w >> 24);
+                    }
+                    for (; k < ll; k++) out[o + k] = src[prev_end + k];
+                }
+                o += ll;
+                const uint32_t offset = pos - cand;
+                out[o] = (uint8_t)offset;
+                out[o + 1] = (uint8_t)(offset >> 8);
+                o += 2;
+                if (mcode >= 15) {
+                    uint32_t r = mcode - 15;
+                    for (; r >= 255; r -= 255) out[o++] = 255;
+                    out[o++] = (uint8_t)r;
+                }
+            }
+            __syncwarp();
+            unsigned big = __ballot_sync(kFull, is_sel && ll >= kCoopLit);
+            while (big) {  // long literal runs: one warp-wide copy each
+                const int l = __ffs(big) - 1;
+                big &= big - 1;
+                warp_copy(out + __shfl_sync(kFull, lit_o, l), src + __shfl_sync(kFull, prev_end, l), __shfl_sync(kFull, ll, l), lane);
+            }
+            op += total;
+            anchor = __shfl_sync(kFull, e_mine, 31 - __clz(sel));
+            ip = max(ip + 32 * step, anchor);
+            nprobe = 1u << kSkipTrigger;
         }
     }
     // last literals

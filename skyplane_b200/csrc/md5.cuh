@@ -5,10 +5,14 @@
 // carries 32 chunks, lane = chunk.  The per-step dependent chain is 3 SASS ops:
 //   LOP3 (F/G/H/I of the newest b) -> IADD3 (+ a + M[g] + K[i], pre-added off the chain)
 //   -> LEA.HI (b + rotl(t, s): ptxas fuses the funnel shift and the add).
-// Message words are staged into shared memory with 16-byte cp.async three blocks ahead of the
-// chain (ring of 4 x 64 B per lane, laid out [slot][piece][lane] so LDS.128 is conflict-free).
+// Message words are staged into shared memory with 16-byte cp.async SKY_MD5_SLOTS-1 blocks ahead of the
+// chain (ring of SKY_MD5_SLOTS x 64 B per lane, laid out [slot][piece][lane] so LDS.128 is conflict-free).
 #pragma once
 #include <stdint.h>
+
+#ifndef SKY_MD5_SLOTS
+#define SKY_MD5_SLOTS 4
+#endif
 
 namespace sky {
 
@@ -132,7 +136,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // fetch a row just ahead of the MD5 lanes and the lanes then hit L2 instead of HBM.
 __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uint64_t len, bool active, uint8_t *out,
                                          unsigned lane, volatile uint32_t *progress) {
-    constexpr int kSlots = 4;  // ring depth (blocks); prefetch distance = kSlots - 1
+    constexpr int kSlots = SKY_MD5_SLOTS;  // ring depth (blocks, power of two); prefetch distance = kSlots - 1
     const uint64_t nfull = active ? (len >> 6) : 0;
     uint64_t wmax = nfull;
 #pragma unroll
