@@ -52,9 +52,11 @@ def run_stream(
     window: int = 512,
     timeout_s: float = 600.0,
     on_done: Optional[Callable[[ChunkRequest], None]] = None,
+    warmup_requests: int = 0,
 ) -> Dict:
     """Stream ``n_requests`` chunk requests (recycling ``pool_files`` by hard link) through the operator.
 
+    The first ``warmup_requests`` completions are not timed (worker start-up: CUDA context, pinned staging).
     Returns {"wall_s", "bytes", "records": [{chunk_id, pool_index, md5, raw_len, frame_path}], "status": {...}}.
     """
     chunk_dir = Path(chunk_dir)
@@ -90,7 +92,7 @@ def run_stream(
                     shutil.copyfile(pool_files[k], dst)
                 pool_of[cid] = k
                 req = ChunkRequest(Chunk(src_key=f"obj/{k}", dest_key=f"obj/{k}", chunk_id=cid, chunk_length_bytes=pool_lens[k], partition_id="0"))
-                if t0 is None:
+                if t0 is None and warmup_requests == 0:
                     t0 = time.perf_counter()
                 store.add_chunk_request(req)
                 sent += 1
@@ -101,7 +103,11 @@ def run_stream(
                 time.sleep(0.0005)
                 continue
             done += 1
-            total_bytes += r.chunk.chunk_length_bytes
+            if done <= warmup_requests:
+                if done == warmup_requests:
+                    t0 = time.perf_counter()
+            else:
+                total_bytes += r.chunk.chunk_length_bytes
             cid = r.chunk.chunk_id
             rec = {
                 "chunk_id": cid,
@@ -136,6 +142,7 @@ def main():
     ap.add_argument("--pool", type=int, default=32)
     ap.add_argument("--workload", choices=["random", "silesia", "mixed"], default="mixed")
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=-1, help="untimed leading requests (default: 4 batches per GPU)")
     ap.add_argument("--dir", default=None)
     a = ap.parse_args()
     from skyplane_b200 import synth
@@ -153,8 +160,10 @@ def main():
         files.append(p)
         lens.append(n)
     try:
-        res = run_stream(base / "chunks", files, lens, a.chunks, n_workers=a.gpus, n_gpus=a.gpus, max_batch_chunks=a.batch,
-                         max_batch_bytes=max(n * a.batch, 64 << 20), keep_frames=False, window=max(256, 4 * a.batch * a.gpus))
+        warm = a.warmup if a.warmup >= 0 else 4 * a.batch * a.gpus
+        res = run_stream(base / "chunks", files, lens, a.chunks + warm, n_workers=a.gpus, n_gpus=a.gpus, max_batch_chunks=a.batch,
+                         max_batch_bytes=max(n * a.batch, 64 << 20), keep_frames=False, window=max(256, 4 * a.batch * a.gpus),
+                         warmup_requests=warm)
         gbs = res["bytes"] / res["wall_s"] / 1e9
         print(json.dumps({"metric": "gateway-queue end-to-end GB/s (raw input)", "value": gbs, "n_gpus": a.gpus, "chunks": a.chunks,
                           "chunk_mib": a.chunk_mib, "wall_s": res["wall_s"], "status": res["status"],

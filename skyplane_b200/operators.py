@@ -128,6 +128,7 @@ class GatewayCompressHash(GatewayOperator):
         max_batch_bytes: int = 512 << 20,
         n_gpus: Optional[int] = None,
         keep_frames_on_disk: bool = True,
+        read_threads: int = 8,
     ):
         super().__init__(handle, region, input_queue, output_queue, error_event, error_queue, chunk_store, n_processes)
         self.use_compression = use_compression
@@ -135,7 +136,9 @@ class GatewayCompressHash(GatewayOperator):
         self.max_batch_bytes = max_batch_bytes
         self.n_gpus = n_gpus
         self.keep_frames_on_disk = keep_frames_on_disk
+        self.read_threads = read_threads
         self._stage = None  # created lazily in the worker process (fork + CUDA)
+        self._readers = None  # thread pool for chunk-file reads, also per process
 
     # -- per-process GPU state ---------------------------------------------------------------
     def _get_stage(self):
@@ -151,6 +154,9 @@ class GatewayCompressHash(GatewayOperator):
         return self._stage
 
     def worker_exit(self, worker_id: int):
+        if self._readers is not None:
+            self._readers.shutdown(wait=True)
+            self._readers = None
         if self._stage is not None:
             self._stage.close()
             self._stage = None
@@ -159,71 +165,134 @@ class GatewayCompressHash(GatewayOperator):
     def process(self, chunk_req: ChunkRequest, *args) -> bool:
         return self.process_batch([chunk_req])[0]
 
-    def process_batch(self, reqs: List[ChunkRequest]) -> List[bool]:
-        """Compress + hash a batch. Returns one bool per request (False = chunk file not ready yet, retry)."""
+    # -- batch plumbing -------------------------------------------------------------------------
+    def _read_into(self, path, view, n: int) -> bool:
+        """Read exactly n bytes of a chunk file into pinned memory; False if the file is not complete yet."""
+        try:
+            with open(path, "rb", buffering=0) as f:
+                got = 0
+                while got < n:
+                    r = f.readinto(view[got:])
+                    if not r:
+                        return False
+                    got += r
+                return not f.read(1)
+        except FileNotFoundError:
+            return False
+
+    def _launch(self, reqs: List[ChunkRequest]):
+        """Stage as many of `reqs` as fit one slot and launch them.
+        -> (slot or None, launched indices, not-ready indices, leftover indices)"""
         stage = self._get_stage()
-        ok = [True] * len(reqs)
-        pending = list(range(len(reqs)))
-        while pending:
-            slot = stage.begin()
-            batch = []
-            rest = []
-            for i in pending:
-                chunk = reqs[i].chunk
-                path = self.chunk_store.get_chunk_file_path(chunk.chunk_id)
-                n = chunk.chunk_length_bytes
-                if n > stage.max_batch_bytes:
-                    raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds the stage's max_batch_bytes")
-                if not path.exists() or os.path.getsize(path) != n:
-                    ok[i] = False  # upstream has not finished writing it (gateway_operator.py:131-150 semantics)
-                    continue
-                if not stage.fits(slot, n):
-                    rest.append(i)
-                    continue
-                stage.add_file(slot, path, n)
-                batch.append(i)
-            if not batch:
-                stage._free.append(slot)
-                if rest:
-                    raise RuntimeError("staging slot cannot hold a single chunk")
-                break
+        slot = stage.begin()
+        launched, not_ready, leftover, jobs = [], [], [], []
+        for i, r in enumerate(reqs):
+            chunk = r.chunk
+            n = chunk.chunk_length_bytes
+            if n > stage.max_batch_bytes:
+                stage.release(slot)
+                raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds the stage's max_batch_bytes")
+            path = self.chunk_store.get_chunk_file_path(chunk.chunk_id)
+            try:
+                ready = os.stat(path).st_size == n  # upstream writes the file before queueing (gateway_operator.py:567-570)
+            except FileNotFoundError:
+                ready = False
+            if not ready:
+                not_ready.append(i)
+            elif not stage.fits(slot, n):
+                leftover.append(i)
+            else:
+                jobs.append((i, path, slot.reserve(n), n))
+        if jobs:
+            # file -> pinned memory copies release the GIL: read the batch with a few threads
+            if self._readers is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._readers = ThreadPoolExecutor(max_workers=self.read_threads)
+            oks = list(self._readers.map(lambda j: self._read_into(j[1], j[2], j[3]), jobs))
+            if not all(oks):  # a file changed under us: retry the whole batch later rather than hash partial data
+                stage.release(slot)
+                return None, [], [j[0] for j in jobs] + not_ready, leftover
+            launched = [j[0] for j in jobs]
             stage.launch(slot)
-            results = stage.collect(slot)
-            for i, r in zip(batch, results):
-                chunk = reqs[i].chunk
-                chunk.md5_hash = r.md5
-                if self.keep_frames_on_disk:
-                    with open(self.chunk_store.get_compressed_file_path(chunk.chunk_id), "wb") as f:
-                        f.write(r.frame)
-                reqs[i]._stage_meta = {"compressed_size_bytes": r.comp_len, "uncompressed_size_bytes": r.raw_len}
-            pending = rest
+            return slot, launched, not_ready, leftover
+        stage.release(slot)
+        if leftover:
+            raise RuntimeError("staging slot cannot hold a single chunk")
+        return None, [], not_ready, leftover
+
+    def _finish(self, slot, reqs: List[ChunkRequest]):
+        """Collect a launched batch: sets md5_hash, writes frames, attaches the size metadata."""
+        results = self._get_stage().collect(slot)
+        for r, res in zip(reqs, results):
+            chunk = r.chunk
+            chunk.md5_hash = res.md5
+            if self.keep_frames_on_disk:
+                with open(self.chunk_store.get_compressed_file_path(chunk.chunk_id), "wb") as f:
+                    f.write(res.frame)
+            r._stage_meta = {"compressed_size_bytes": res.comp_len, "uncompressed_size_bytes": res.raw_len}
+
+    def process_batch(self, reqs: List[ChunkRequest]) -> List[bool]:
+        """Compress + hash a batch synchronously. One bool per request (False = chunk file not ready yet, retry)."""
+        ok = [True] * len(reqs)
+        todo = list(range(len(reqs)))
+        while todo:
+            sub = [reqs[i] for i in todo]
+            slot, launched, not_ready, leftover = self._launch(sub)
+            for k in not_ready:
+                ok[todo[k]] = False
+            if slot is not None:
+                self._finish(slot, [sub[k] for k in launched])
+            todo = [todo[k] for k in leftover]
         return ok
 
+    def _complete(self, worker_id: int, r: ChunkRequest):
+        meta = r.__dict__.pop("_stage_meta", None)
+        self.chunk_store.log_chunk_state(r, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id, metadata=meta)
+        if self.output_queue is not None:
+            self.output_queue.put(r)
+
     def worker_loop(self, worker_id: int, *args):
-        """Batch-draining loop with the reference's logging / error conventions."""
+        """Batch-draining, double-buffered loop with the reference's logging / error conventions: while the GPU
+        works on one batch the next one is read from the chunk files into the other staging slot."""
         self.worker_id = worker_id
-        while self._running(worker_id):
-            try:
-                reqs = self.input_queue.get_batch_nowait(self.max_batch_chunks, self.handle)
-                if not reqs:
-                    time.sleep(0.0005)
-                    continue
-                for r in reqs:
-                    self.chunk_store.log_chunk_state(r, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
-                oks = self.process_batch(reqs)
-                retry = []
-                for r, ok in zip(reqs, oks):
-                    if ok:
-                        meta = r.__dict__.pop("_stage_meta", None)
-                        self.chunk_store.log_chunk_state(r, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id, metadata=meta)
-                        if self.output_queue is not None:
-                            self.output_queue.put(r)
-                    else:
-                        retry.append(r)
-                if retry:
-                    time.sleep(0.1)
-                    for r in retry:
-                        self.input_queue.put(r)
-            except Exception as e:
-                self._fail(worker_id, e)
-        self.worker_exit(worker_id)
+        inflight = []  # [(slot, reqs)] oldest first
+        backlog: List[ChunkRequest] = []  # dequeued but not yet launched (did not fit the slot)
+        try:
+            while self._running(worker_id):
+                try:
+                    stage_free = self._stage is None or bool(self._stage._free)
+                    if stage_free:
+                        room = self.max_batch_chunks - len(backlog)
+                        fresh = self.input_queue.get_batch_nowait(room, self.handle) if room > 0 else []
+                        for r in fresh:
+                            self.chunk_store.log_chunk_state(r, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
+                        cand = backlog + fresh
+                        if cand:
+                            slot, launched, not_ready, leftover = self._launch(cand)
+                            if slot is not None:
+                                inflight.append((slot, [cand[k] for k in launched]))
+                            backlog = [cand[k] for k in leftover]
+                            if not_ready:
+                                time.sleep(0.1 if slot is None and not inflight else 0)
+                                for k in not_ready:
+                                    self.input_queue.put(cand[k])
+                            if slot is not None and len(inflight) < 2:
+                                continue  # try to get a second batch going before blocking on the first
+                    if inflight:
+                        slot, reqs = inflight.pop(0)
+                        self._finish(slot, reqs)
+                        for r in reqs:
+                            self._complete(worker_id, r)
+                    elif not backlog:
+                        time.sleep(0.0005)
+                except Exception as e:
+                    self._fail(worker_id, e)
+            # drain what is already on the GPU so no accepted chunk is lost on a clean stop
+            if not self.error_event.is_set():
+                for slot, reqs in inflight:
+                    self._finish(slot, reqs)
+                    for r in reqs:
+                        self._complete(worker_id, r)
+        finally:
+            self.worker_exit(worker_id)

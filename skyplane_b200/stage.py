@@ -81,6 +81,11 @@ class ChunkStage:
         s.reset()
         return s
 
+    def release(self, slot: _Slot):
+        """Give back a slot taken with begin() that was never launched."""
+        slot.reset()
+        self._free.append(slot)
+
     def fits(self, slot: _Slot, n: int) -> bool:
         return (
             len(slot.lens) < self.max_chunks
@@ -143,7 +148,7 @@ class ChunkStage:
                 self.add_bytes(slot, chunks[j])
                 j += 1
             if j == i:
-                self._free.append(slot)
+                self.release(slot)
                 raise native.SkyChunkError(native.SKY_E_CAPACITY, f"chunk of {memoryview(chunks[i]).nbytes} bytes exceeds max_batch_bytes")
             self.launch(slot)
             for r in self.collect(slot):
