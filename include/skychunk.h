@@ -97,6 +97,27 @@ SKY_API int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, cons
                        void *d_dst, const uint64_t *dst_off, const uint64_t *dst_cap, uint32_t flags, void *stream,
                        uint64_t *out_len, uint8_t *md5, float *kernel_ms);
 
+/* ---- receiver side: LZ4 frame decode + digest of the decoded bytes -----------------------------------
+ * Replaces lz4.frame.decompress(to_write) (skyplane/gateway/operators/gateway_receiver.py:195-201) and supplies
+ * the digest for the "# todo check hash" at gateway_receiver.py:231.  raw_len[i] is the expected decoded size
+ * (WireProtocolHeader.raw_data_len, skyplane/chunk.py:100).  Accepts the frames this library emits (independent
+ * 64 KiB blocks) and the reference sender's (linked blocks); status[i] = 0 or a SKY_D_* code (a bad frame is an
+ * error status, never a crash); md5[16*i..] = MD5 of the decoded bytes.
+ * sky_decode_device: frames and output already in HBM (out_off multiples of 16).  sky_decode: host buffers,
+ * synchronous, through slot 0's slabs (needs n_slots >= 1). */
+#define SKY_D_OK 0
+#define SKY_D_BAD_HEADER (-1)
+#define SKY_D_CORRUPT (-2)
+#define SKY_D_SIZE (-3)
+#define SKY_D_UNSUPPORTED (-4)
+#define SKY_D_LAYOUT (-5)
+#define SKY_D_TRUNCATED (-6)
+SKY_API int sky_decode_device(sky_ctx *ctx, uint32_t n, const void *d_frames, const uint64_t *frame_off, const uint64_t *frame_len,
+                      void *d_out, const uint64_t *out_off, const uint64_t *raw_len, void *stream, int32_t *status, uint8_t *md5,
+                      float *kernel_ms);
+SKY_API int sky_decode(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
+               const uint64_t *raw_len, int32_t *status, uint8_t *md5, float *kernel_ms);
+
 /* Device-memory helpers so a host without torch can drive the device path. */
 SKY_API int sky_device_alloc(sky_ctx *ctx, uint64_t bytes, void **dptr);
 SKY_API int sky_device_free(sky_ctx *ctx, void *dptr);

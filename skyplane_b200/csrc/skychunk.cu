@@ -38,6 +38,7 @@
 
 #include "../../include/skychunk.h"
 #include "lz4.cuh"
+#include "lz4dec.cuh"
 #include "md5.cuh"
 
 namespace sky {
@@ -233,6 +234,72 @@ __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) 
     }
 }
 
+
+// ------------------------------------------------------------------------------------ receiver side
+struct DecParams {
+    DecChunk *chunks;
+    DecBlock *blocks;
+    int32_t *status;     // per chunk, 0 = ok (mapped host memory)
+    uint32_t *done;      // per chunk: leading blocks fully decoded (linked frames wait on it)
+    uint32_t *counter;   // work counter
+    uint32_t n_chunks;
+    uint32_t rows;
+};
+
+__global__ void sky_frame_index_kernel(const DecParams p) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= p.n_chunks) return;
+    DecChunk cd = p.chunks[c];
+    int32_t st = kDecOk;
+    frame_index(cd, p.blocks + cd.blk_base, &st);
+    p.chunks[c].linked = cd.linked;
+    p.status[c] = st;
+}
+
+__global__ void __launch_bounds__(512, 1) sky_decode_kernel(const DecParams p) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t total = p.rows * p.n_chunks;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(p.counter, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= total) break;
+        const uint32_t c = w % p.n_chunks, j = w / p.n_chunks;
+        const DecChunk cd = p.chunks[c];
+        if (j >= cd.nblk) continue;
+        int32_t st = *reinterpret_cast<volatile int32_t *>(p.status + c);
+        const uint64_t pos = (uint64_t)j * kBlock;
+        const uint32_t want = (uint32_t)min((uint64_t)kBlock, cd.raw_len - pos);
+        if (cd.linked) {  // matches may reach into earlier blocks: decode in order within the chunk
+            if (lane == 0) {
+                unsigned ns = 64;
+                while (ld_acquire32(p.done + c) < j) {
+                    __nanosleep(ns);
+                    if (ns < 2048) ns <<= 1;
+                }
+            }
+            __syncwarp();
+            st = *reinterpret_cast<volatile int32_t *>(p.status + c);
+        }
+        if (st == kDecOk) {
+            const DecBlock b = p.blocks[cd.blk_base + j];
+            const uint32_t sz = b.word & 0x7FFFFFFFu;
+            if (b.word & 0x80000000u) {
+                if (sz != want) st = kDecLayout;
+                else warp_copy(cd.out + pos, cd.frame + b.off, sz, lane);
+            } else {
+                st = lz4_decode_block(cd.frame + b.off, sz, cd.out, pos, want, cd.linked ? 0 : pos, lane);
+            }
+            if (st != kDecOk && lane == 0) atomicMin(p.status + c, st);
+        }
+        __syncwarp();
+        if (cd.linked && lane == 0) {
+            __threadfence();
+            st_release32(p.done + c, j + 1);
+        }
+    }
+}
+
 }  // namespace sky
 
 // ======================================================================================= host side
@@ -255,6 +322,11 @@ struct Slot {
     uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;  // input landed (on ctx->st_h2d) / frames landed (on ctx->st_d2h)
     uint32_t *d_counters = nullptr;
+    // receiver side
+    DecChunk *h_dchunks = nullptr, *d_dchunks = nullptr;
+    DecBlock *d_dblocks = nullptr;
+    uint64_t dblocks_cap = 0;
+    int32_t *h_dstatus = nullptr, *d_dstatus = nullptr;  // pinned host mirror / device array
     // in-flight ticket
     bool busy = false;
     uint64_t ticket = 0;
@@ -349,6 +421,10 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
     CK(ctx, cudaMalloc(&s.d_counters, 64));
+    CK(ctx, cudaMallocHost(&s.h_dchunks, nc * sizeof(DecChunk)));
+    CK(ctx, cudaMalloc(&s.d_dchunks, nc * sizeof(DecChunk)));
+    CK(ctx, cudaMallocHost(&s.h_dstatus, nc * sizeof(int32_t)));
+    CK(ctx, cudaMalloc(&s.d_dstatus, nc * sizeof(int32_t)));
     CK(ctx, cudaMalloc(&s.d_freed, nc * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_progress, (ng / 32 + 1) * sizeof(uint32_t)));
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -364,7 +440,8 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
 static void free_slot(Slot &s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
-    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters); cudaFree(s.d_freed); cudaFree(s.d_progress);
+    cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters);
+    cudaFreeHost(s.h_dchunks); cudaFree(s.d_dchunks); cudaFree(s.d_dblocks); cudaFreeHost(s.h_dstatus); cudaFree(s.d_dstatus); cudaFree(s.d_freed); cudaFree(s.d_progress);
     cudaFree(s.d_in); cudaFree(s.d_out);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -672,6 +749,115 @@ int sky_memcpy_d2h(sky_ctx *ctx, void *host, const void *dptr, uint64_t bytes) {
     if (!ctx) return SKY_E_INVALID;
     CK(ctx, cudaSetDevice(ctx->device));
     CK(ctx, cudaMemcpy(host, dptr, bytes, cudaMemcpyDeviceToHost));
+    return SKY_OK;
+}
+
+
+// ---------------------------------------------------------------------------------- receiver side
+// Enqueues index + decode (+ MD5 of the decoded bytes through the fused kernel's MD5 role) on `st`.
+static int launch_decode(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, const uint8_t *d_frames, const uint64_t *frame_off,
+                         const uint64_t *frame_len, uint8_t *d_out, const uint64_t *out_off, const uint64_t *raw_len) {
+    uint64_t nblk_total = 0;
+    uint32_t rows = 1;
+    for (uint32_t i = 0; i < n; i++) {
+        DecChunk &d = s.h_dchunks[i];
+        d.frame = d_frames + frame_off[i];
+        d.out = d_out + out_off[i];
+        d.frame_len = frame_len[i];
+        d.raw_len = raw_len[i];
+        const uint64_t nb = (raw_len[i] + kBlock - 1) / kBlock;
+        if (nb >= (1ull << 24)) return SKY_E_CAPACITY;
+        d.nblk = (uint32_t)nb;
+        d.blk_base = nblk_total;
+        d.linked = 0;
+        nblk_total += nb;
+        rows = std::max(rows, d.nblk);
+    }
+    if ((uint64_t)rows * n >= 0xffffffffull) return SKY_E_CAPACITY;
+    if (nblk_total + 1 > s.dblocks_cap) {
+        CK(ctx, cudaStreamSynchronize(st));
+        cudaFree(s.d_dblocks);
+        s.d_dblocks = nullptr;
+        s.dblocks_cap = 0;
+        CK(ctx, cudaMalloc(&s.d_dblocks, (nblk_total + 1) * sizeof(DecBlock)));
+        s.dblocks_cap = nblk_total + 1;
+    }
+    CK(ctx, cudaMemcpyAsync(s.d_dchunks, s.h_dchunks, n * sizeof(DecChunk), cudaMemcpyHostToDevice, st));
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
+    CK(ctx, cudaMemsetAsync(s.d_freed, 0, n * sizeof(uint32_t), st));
+    CK(ctx, cudaMemsetAsync(s.d_dstatus, 0, n * sizeof(int32_t), st));
+    DecParams p;
+    p.chunks = s.d_dchunks;
+    p.blocks = s.d_dblocks;
+    p.status = s.d_dstatus;
+    p.done = s.d_freed;
+    p.counter = s.d_counters;
+    p.n_chunks = n;
+    p.rows = rows;
+    CK(ctx, cudaEventRecord(s.ev_h0, st));  // start marker of the receiver-side kernels
+    sky_frame_index_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    sky_decode_kernel<<<ctx->sm_count, 512, 0, st>>>(p);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    CK(ctx, cudaMemcpyAsync(s.h_dstatus, s.d_dstatus, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    return SKY_OK;
+}
+
+int sky_decode_device(sky_ctx *ctx, uint32_t n, const void *d_frames, const uint64_t *frame_off, const uint64_t *frame_len,
+                      void *d_out, const uint64_t *out_off, const uint64_t *raw_len, void *stream, int32_t *status, uint8_t *md5,
+                      float *kernel_ms) {
+    if (!ctx || n == 0 || !d_frames || !frame_off || !frame_len || !out_off || !raw_len) return SKY_E_INVALID;
+    if (n > ctx->max_chunks) return SKY_E_CAPACITY;
+    if (reinterpret_cast<uintptr_t>(d_out) & 15) return SKY_E_INVALID;
+    for (uint32_t i = 0; i < n; i++) {
+        if (out_off[i] & 15) return SKY_E_INVALID;
+        if (raw_len[i] && !d_out) return SKY_E_INVALID;
+    }
+    CK(ctx, cudaSetDevice(ctx->device));
+    Slot &s = ctx->slots[0];
+    if (s.busy) return SKY_E_BUSY;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    int rc = launch_decode(ctx, s, st, n, (const uint8_t *)d_frames, frame_off, frame_len, (uint8_t *)d_out, out_off, raw_len);
+    if (rc != SKY_OK) return rc;
+    // MD5 over the decoded output: same kernel, MD5 role only (src = decoded regions; dst unused)
+    std::vector<uint64_t> dst_off(n, 0);
+    rc = launch_batch(ctx, s, st, st, n, (const uint8_t *)d_out, out_off, raw_len, (uint8_t *)d_out, dst_off.data(), SKY_F_MD5);
+    if (rc != SKY_OK) return rc;
+    CK(ctx, cudaStreamSynchronize(st));
+    if (status) memcpy(status, s.h_dstatus, n * sizeof(int32_t));
+    if (md5) memcpy(md5, s.h_md5, (size_t)n * 16);
+    if (kernel_ms) CK(ctx, cudaEventElapsedTime(kernel_ms, s.ev_h0, s.ev_k1));  // index + decode + MD5
+    return SKY_OK;
+}
+
+int sky_decode(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
+               const uint64_t *raw_len, int32_t *status, uint8_t *md5, float *kernel_ms) {
+    if (!ctx || n == 0 || !frames || !frame_len || !dst || !raw_len) return SKY_E_INVALID;
+    if (n > ctx->max_chunks) return SKY_E_CAPACITY;
+    Slot &s = ctx->slots[0];
+    if (s.busy) return SKY_E_BUSY;
+    if (!s.d_in) return SKY_E_INVALID;  // ctx created without slabs
+    CK(ctx, cudaSetDevice(ctx->device));
+    // roles swap on the way back: frames (<= bound) go into the frame slab, decoded bytes into the input slab
+    std::vector<uint64_t> f_off(n), o_off(n);
+    uint64_t fp = 0, op = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!frames[i] || (raw_len[i] && !dst[i])) return SKY_E_INVALID;
+        f_off[i] = fp;
+        o_off[i] = op;
+        fp += round16(frame_len[i]);
+        op += round16(raw_len[i]);
+    }
+    if (fp > ctx->out_cap || op > ctx->in_cap) return SKY_E_CAPACITY;
+    for (uint32_t i = 0; i < n; i++)
+        CK(ctx, cudaMemcpyAsync(s.d_out + f_off[i], frames[i], frame_len[i], cudaMemcpyHostToDevice, s.stream));
+    int rc = sky_decode_device(ctx, n, s.d_out, f_off.data(), frame_len, s.d_in, o_off.data(), raw_len, s.stream, status, md5, kernel_ms);
+    if (rc != SKY_OK) return rc;
+    for (uint32_t i = 0; i < n; i++)
+        if (raw_len[i] && s.h_dstatus[i] == 0)
+            CK(ctx, cudaMemcpyAsync(dst[i], s.d_in + o_off[i], raw_len[i], cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaStreamSynchronize(s.stream));
     return SKY_OK;
 }
 

@@ -15,12 +15,16 @@ LIB_PATH = _PKG / "libskychunk.so"
 SKY_OK = 0
 SKY_E_INVALID, SKY_E_NOGPU, SKY_E_CUDA, SKY_E_CAPACITY, SKY_E_BUSY, SKY_E_TICKET, SKY_E_NOMEM = -1, -2, -3, -4, -5, -6, -7
 F_LZ4, F_MD5, F_MD5_EXCLUSIVE, F_NO_PACING = 1, 2, 4, 8
+# sky_decode status codes
+D_OK, D_BAD_HEADER, D_CORRUPT, D_SIZE, D_UNSUPPORTED, D_LAYOUT, D_TRUNCATED = 0, -1, -2, -3, -4, -5, -6
+D_NAMES = {0: "ok", -1: "bad frame header", -2: "corrupt block", -3: "size mismatch", -4: "unsupported frame feature",
+           -5: "unexpected block layout", -6: "truncated frame"}
 
 # every symbol include/skychunk.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = (
     "sky_strerror", "sky_last_error", "sky_abi_version", "sky_device_count", "sky_frame_bound",
     "sky_ctx_create", "sky_ctx_destroy", "sky_pinned_alloc", "sky_pinned_free",
-    "sky_submit", "sky_wait", "sky_process_device",
+    "sky_submit", "sky_wait", "sky_process_device", "sky_decode_device", "sky_decode",
     "sky_device_alloc", "sky_device_free", "sky_memcpy_h2d", "sky_memcpy_d2h", "sky_launch_count",
 )
 
@@ -86,6 +90,11 @@ def lib() -> ctypes.CDLL:
     L.sky_wait.restype = i32
     L.sky_process_device.argtypes = [vp, u32, vp, p_u64, p_u64, vp, p_u64, p_u64, u32, vp, p_u64, vp, ctypes.POINTER(ctypes.c_float)]
     L.sky_process_device.restype = i32
+    p_i32 = ctypes.POINTER(ctypes.c_int32)
+    L.sky_decode_device.argtypes = [vp, u32, vp, p_u64, p_u64, vp, p_u64, p_u64, vp, p_i32, vp, ctypes.POINTER(ctypes.c_float)]
+    L.sky_decode_device.restype = i32
+    L.sky_decode.argtypes = [vp, u32, ctypes.POINTER(vp), p_u64, ctypes.POINTER(vp), p_u64, p_i32, vp, ctypes.POINTER(ctypes.c_float)]
+    L.sky_decode.restype = i32
     L.sky_device_alloc.argtypes = [vp, u64, ctypes.POINTER(vp)]
     L.sky_device_alloc.restype = i32
     L.sky_device_free.argtypes = [vp, vp]
@@ -218,6 +227,32 @@ class Context:
         )
         raw = bytes(md5)
         return list(out), [raw[16 * i : 16 * i + 16] for i in range(n)], ms.value
+
+    # ------------------------------------------------------------------ receiver side
+    def decode_device(self, d_frames: int, frame_off: Sequence[int], frame_len: Sequence[int], d_out: int, out_off: Sequence[int],
+                      raw_len: Sequence[int], stream: int = 0):
+        """-> (status: list[int], digests: list[bytes], kernel_ms)."""
+        n = len(frame_len)
+        U = ctypes.c_uint64 * n
+        st = (ctypes.c_int32 * n)()
+        md5 = (ctypes.c_ubyte * (16 * n))()
+        ms = ctypes.c_float(0)
+        self._check(lib().sky_decode_device(self._h, n, d_frames, U(*frame_off), U(*frame_len), d_out, U(*out_off), U(*raw_len),
+                                            stream or None, st, md5, ctypes.byref(ms)))
+        raw = bytes(md5)
+        return list(st), [raw[16 * i : 16 * i + 16] for i in range(n)], ms.value
+
+    def decode(self, frame_addrs: Sequence[int], frame_lens: Sequence[int], dst_addrs: Sequence[int], raw_lens: Sequence[int]):
+        """Host buffers, synchronous. -> (status, digests, kernel_ms)."""
+        n = len(frame_addrs)
+        A = ctypes.c_void_p * n
+        U = ctypes.c_uint64 * n
+        st = (ctypes.c_int32 * n)()
+        md5 = (ctypes.c_ubyte * (16 * n))()
+        ms = ctypes.c_float(0)
+        self._check(lib().sky_decode(self._h, n, A(*frame_addrs), U(*frame_lens), A(*dst_addrs), U(*raw_lens), st, md5, ctypes.byref(ms)))
+        raw = bytes(md5)
+        return list(st), [raw[16 * i : 16 * i + 16] for i in range(n)], ms.value
 
     # ------------------------------------------------------------------ torch-free device memory
     def device_alloc(self, nbytes: int) -> int:

@@ -296,3 +296,63 @@ class GatewayCompressHash(GatewayOperator):
                         self._complete(worker_id, r)
         finally:
             self.worker_exit(worker_id)
+
+
+class ChecksumMismatchException(Exception):
+    """Same name as skyplane/exceptions.py:44-48: the decoded chunk's MD5 differs from Chunk.md5_hash."""
+
+
+class GatewayDecompressVerify(GatewayOperator):
+    """Receiving side: what gateway_receiver.py:191-233 does after the socket read.
+
+    ``<chunk_id>.chunk.lz4`` (the wire payload) -> LZ4 frame decode on the GPU -> ``<chunk_id>.chunk`` of exactly
+    ``chunk_length_bytes`` bytes (the size check at gateway_receiver.py:213-218), and -- closing the reference's
+    "# todo check hash" (gateway_receiver.py:231) -- the digest of the decoded bytes is compared with
+    ``chunk.md5_hash`` when the sender supplied one.  A corrupt frame or a digest mismatch raises, which stops the
+    gateway through ``error_event`` like any other operator failure."""
+
+    def __init__(self, *args, max_batch_chunks: int = 64, max_batch_bytes: int = 512 << 20, n_gpus: Optional[int] = None,
+                 remove_frames: bool = True, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.max_batch_chunks = max_batch_chunks
+        self.max_batch_bytes = max_batch_bytes
+        self.n_gpus = n_gpus
+        self.remove_frames = remove_frames
+        self._stage = None
+
+    def _get_stage(self):
+        if self._stage is None:
+            from skyplane_b200 import native
+            from skyplane_b200.stage import ChunkStage
+
+            ngpu = self.n_gpus or native.device_count()
+            if ngpu <= 0:
+                raise native.SkyChunkError(native.SKY_E_NOGPU, "GatewayDecompressVerify needs a CUDA device; there is no CPU fallback")
+            self._stage = ChunkStage((self.worker_id or 0) % ngpu, self.max_batch_bytes, self.max_batch_chunks, n_slots=1)
+        return self._stage
+
+    def worker_exit(self, worker_id: int):
+        if self._stage is not None:
+            self._stage.close()
+            self._stage = None
+
+    def process(self, chunk_req: ChunkRequest, *args) -> bool:
+        from skyplane_b200 import native
+
+        chunk = chunk_req.chunk
+        fpath = self.chunk_store.get_compressed_file_path(chunk.chunk_id)
+        if not fpath.exists():
+            return False  # payload not received yet: retry (GatewayWaitReceiver semantics, gateway_operator.py:131-150)
+        frame = fpath.read_bytes()
+        (data, digest, status), = self._get_stage().decode([frame], [chunk.chunk_length_bytes])
+        if status != 0:
+            raise ValueError(f"chunk {chunk.chunk_id}: LZ4 frame rejected ({native.D_NAMES.get(status, status)})")
+        if chunk.md5_hash is not None and bytes(chunk.md5_hash) != digest:
+            raise ChecksumMismatchException(f"chunk {chunk.chunk_id}: md5 {digest.hex()} != expected {bytes(chunk.md5_hash).hex()}")
+        with open(self.chunk_store.get_chunk_file_path(chunk.chunk_id), "wb") as f:
+            f.write(data)
+        if chunk.md5_hash is None:
+            chunk.md5_hash = digest  # lets the upload step send Content-MD5 (gateway_operator.py:640)
+        if self.remove_frames:
+            fpath.unlink(missing_ok=True)
+        return True

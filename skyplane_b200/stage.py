@@ -156,6 +156,39 @@ class ChunkStage:
             i = j
         return out
 
+    # ------------------------------------------------------------------ receiver side
+    def decode(self, frames: Sequence[BytesLike], raw_lens: Sequence[int]):
+        """Decode LZ4 frames and digest the decoded bytes (gateway_receiver.py:195-201 + the missing hash check).
+        -> list of (data: bytes | None, md5: bytes, status: int); data is None when status != 0."""
+        out = []
+        i = 0
+        if self._free is None or not self._free:
+            raise native.SkyChunkError(native.SKY_E_BUSY, "collect() pending batches before decode()")
+        slot = self._free[-1]  # its pinned buffers are idle: frames are staged in `out`, decoded bytes land in `inp`
+        while i < len(frames):
+            f_off, o_off, fp, op = [], [], 0, 0
+            j = i
+            while j < len(frames) and j - i < self.max_chunks:
+                fl, rl = memoryview(frames[j]).nbytes, raw_lens[j]
+                if fp + native.round16(fl) > slot.out.nbytes or op + native.round16(rl) > slot.inp.nbytes:
+                    break
+                slot.out.view[fp : fp + fl] = memoryview(frames[j]).cast("B")
+                f_off.append(fp)
+                o_off.append(op)
+                fp += native.round16(fl)
+                op += native.round16(rl)
+                j += 1
+            if j == i:
+                raise native.SkyChunkError(native.SKY_E_CAPACITY, "frame exceeds the stage's staging buffers")
+            lens = [memoryview(frames[k]).nbytes for k in range(i, j)]
+            raws = list(raw_lens[i:j])
+            st, dg, self.last_kernel_ms = self.ctx.decode([slot.out.addr + o for o in f_off], lens, [slot.inp.addr + o for o in o_off], raws)
+            for k in range(j - i):
+                data = bytes(slot.inp.view[o_off[k] : o_off[k] + raws[k]]) if st[k] == 0 else None
+                out.append((data, dg[k], st[k]))
+            i = j
+        return out
+
     def close(self):
         self.ctx.close()
         for s in self._slots:
