@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--workloads", default="random,silesia")
     ap.add_argument("--flags", default="lz4,md5,both,both_excl")
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--decode", action="store_true", help="also time the receiver-side decode + MD5 of the frames")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     FL = {"lz4": native.F_LZ4, "md5": native.F_MD5, "both": 0, "both_excl": native.F_MD5_EXCLUSIVE, "md5_excl": native.F_MD5 | native.F_MD5_EXCLUSIVE,
@@ -69,6 +70,20 @@ def main():
                 tot = n * chunk_bytes
                 print(json.dumps({"workload": wl, "chunk_mib": float(sz), "chunks": n, "flags": fl, "kernel_ms": k, "raw_input_gbs": tot / k / 1e6,
                                   "ratio": (tot / sum(out_lens)) if sum(out_lens) else None, "per_stream_gbs": chunk_bytes / k / 1e6}), flush=True)
+            if a.decode:
+                # receiver side: decode the frames just produced (d_out) back into a fresh buffer + MD5 of the result
+                out_lens, dg, _ = ctx.process_device(d_in.data_ptr(), src_off, [chunk_bytes] * n, d_out.data_ptr(), dst_off, [bound] * n, 0, 0)
+                d_back = torch.empty_like(d_in)
+                ms = []
+                for it in range(a.iters + 1):
+                    st, dg2, kms = ctx.decode_device(d_out.data_ptr(), dst_off, out_lens, d_back.data_ptr(), src_off, [chunk_bytes] * n, 0)
+                    if it:
+                        ms.append(kms)
+                ok = all(x == 0 for x in st) and dg2 == dg and bool(torch.equal(d_back[: n * stride - (stride - chunk_bytes)], d_in[: n * stride - (stride - chunk_bytes)]))
+                k = statistics.median(ms)
+                print(json.dumps({"workload": wl, "chunk_mib": float(sz), "chunks": n, "flags": "decode+md5", "kernel_ms": k,
+                                  "raw_output_gbs": n * chunk_bytes / k / 1e6, "roundtrip_ok": ok}), flush=True)
+                del d_back
             ctx.close()
             del d_in, d_out
             torch.cuda.empty_cache()
