@@ -235,6 +235,9 @@ def run_gpu(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the stage has no CPU fallback (use --impl reference for the CPU arm)")
+    from skyplane_b200.numa import bind_to_gpu
+
+    numa_node = bind_to_gpu(local) if world > 1 else None  # pinned staging on the GPU's own socket
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -415,7 +418,7 @@ def run_gpu(args):
             "config": {"workload": f"{n_chunks} x {args.chunk_mib} MiB {args.workload} chunks per GPU, one fused LZ4-frame+MD5 launch per step",
                        "chunks_per_gpu": n_chunks, "chunk_bytes": chunk_bytes, "parallelism": f"chunk-sharded x{world}, no collective",
                        "l2": "inputs (8 GiB/GPU) far exceed the 126 MB L2; no explicit flush", "compression_ratio": ratio,
-                       "md5_exclusive_subpartition": bool(args.md5_exclusive)},
+                       "md5_exclusive_subpartition": bool(args.md5_exclusive), "numa_node_rank0": numa_node},
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

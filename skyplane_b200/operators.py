@@ -150,6 +150,10 @@ class GatewayCompressHash(GatewayOperator):
             if ngpu <= 0:
                 raise native.SkyChunkError(native.SKY_E_NOGPU, "GatewayCompressHash needs a CUDA device; there is no CPU fallback")
             device = (self.worker_id or 0) % ngpu
+            if ngpu > 1:
+                from skyplane_b200.numa import bind_to_gpu
+
+                bind_to_gpu(device)  # pinned staging buffers on the GPU's own socket
             self._stage = ChunkStage(device, self.max_batch_bytes, self.max_batch_chunks, n_slots=2)
         return self._stage
 
