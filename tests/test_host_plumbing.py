@@ -274,3 +274,120 @@ def test_world_size_2_gloo_max_over_ranks():
     assert res[0][1] == [0, 2, 4, 6, 8, 10] and res[1][1] == [1, 3, 5, 7, 9]
     assert res[0][2] == res[1][2] == 2.0  # MAX over ranks
     assert res[0][3] == res[1][3] == 11.0  # every unit counted once
+
+
+# ------------------------------------------------------------------ GatewayCompressHash host logic with a stub stage (no GPU)
+class _StubSlot:
+    def __init__(self, cap):
+        self.buf = bytearray(cap)
+        self.reset()
+
+    def reset(self):
+        self.spans, self.used = [], 0
+
+    def reserve(self, n):
+        off = self.used
+        self.spans.append((off, n))
+        self.used += n
+        return memoryview(self.buf)[off : off + n]
+
+
+class _StubStage:
+    """Test double with ChunkStage's staging API; 'computes' with hashlib + the oracle (tests may use the oracle)."""
+
+    def __init__(self, cap=4 << 20, max_chunks=4, n_slots=2):
+        self.max_batch_bytes, self.max_chunks = cap, max_chunks
+        self._free = [_StubSlot(cap) for _ in range(n_slots)]
+        self.launched = 0
+
+    def begin(self):
+        s = self._free.pop()
+        s.reset()
+        return s
+
+    def release(self, slot):
+        self._free.append(slot)
+
+    def fits(self, slot, n):
+        return len(slot.spans) < self.max_chunks and slot.used + n <= len(slot.buf)
+
+    def launch(self, slot):
+        self.launched += 1
+        return slot
+
+    def collect(self, slot):
+        import hashlib
+
+        import oracle
+        from skyplane_b200.stage import StageResult
+
+        out = []
+        for off, n in slot.spans:
+            data = bytes(slot.buf[off : off + n])
+            frame = oracle.lz4f_compress_indep(data)
+            out.append(StageResult(frame=memoryview(frame), md5=hashlib.md5(data).digest(), raw_len=n, comp_len=len(frame)))
+        self._free.append(slot)
+        return out
+
+    def close(self):
+        pass
+
+
+class _StubbedCompressHash(GatewayCompressHash):
+    def _get_stage(self):
+        if self._stage is None:
+            self._stage = _StubStage()
+        return self._stage
+
+
+def test_compress_hash_worker_loop_with_stub_stage(tmp_path):
+    import hashlib
+
+    import oracle
+
+    cs = ChunkStore(tmp_path)
+    qin, qout = GatewayQueue(), GatewayQueue()
+    err_ev, err_q = mp.Event(), mp.Queue()
+    op = _StubbedCompressHash("ch", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=4, read_threads=2)
+    datas = {("%02x" % i) * 16: os.urandom(1000 + 37 * i) + bytes(5000) for i in range(11)}
+    datas["ee" * 16] = b""  # zero-length chunk (gateway_operator.py:544-548)
+    late = "dd" * 16
+    datas[late] = b"late chunk " * 500
+    for cid, d in datas.items():
+        if cid != late:
+            cs.get_chunk_file_path(cid).write_bytes(d)
+    op.start_workers()
+    try:
+        for cid, d in datas.items():
+            qin.put(ChunkRequest(Chunk("k", "k", cid, len(d), partition_id="0")))
+        got = _drain(qout, len(datas) - 1, timeout=20)
+        assert len(got) == len(datas) - 1  # the late chunk keeps being re-queued (process -> False semantics)
+        cs.get_chunk_file_path(late).write_bytes(datas[late])  # upstream finishes writing it
+        got += _drain(qout, 1, timeout=20)
+        assert sorted(r.chunk.chunk_id for r in got) == sorted(datas)
+        for r in got:
+            d = datas[r.chunk.chunk_id]
+            assert r.chunk.md5_hash == hashlib.md5(d).digest()
+            frame = cs.get_compressed_file_path(r.chunk.chunk_id).read_bytes()
+            assert oracle.lz4f_decode(frame, len(d)) == d
+            assert cs.get_chunk_file_path(r.chunk.chunk_id).exists()  # the stage never deletes the chunk file
+        recs = []
+        t0 = time.time()
+        while time.time() - t0 < 5 and sum(1 for x in recs if x["state"] == "complete") < len(datas):
+            try:
+                recs.append(cs.chunk_status_queue.get(timeout=0.2))
+            except queue.Empty:
+                pass
+        done = [x for x in recs if x["state"] == "complete"]
+        assert len(done) == len(datas)
+        assert all(x["uncompressed_size_bytes"] == len(datas[x["chunk_id"]]) and x["compressed_size_bytes"] > 0 for x in done)
+        # a chunk larger than the stage can ever hold is an error -> gateway-wide stop
+        big = "cc" * 16
+        cs.get_chunk_file_path(big).write_bytes(bytes(5 << 20))
+        qin.put(ChunkRequest(Chunk("k", "k", big, 5 << 20, partition_id="0")))
+        t0 = time.time()
+        while not err_ev.is_set() and time.time() - t0 < 10:
+            time.sleep(0.01)
+        assert err_ev.is_set() and "max_batch_bytes" in err_q.get(timeout=2)
+    finally:
+        op.stop_workers()
