@@ -10,6 +10,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #ifndef SKY_MD5_SLOTS
 #define SKY_MD5_SLOTS 4
 #endif
@@ -134,9 +136,17 @@ __device__ __forceinline__ void cp_async_wait() {
 // Writes 16 digest bytes to `out` for active lanes.
 // `progress` (may be null): lane 0 publishes how many 64 KiB rows the warp has consumed, so LZ4 warps can
 // fetch a row just ahead of the MD5 lanes and the lanes then hit L2 instead of HBM.
+// `gate(row, wants)`: called (warp-converged) before the first byte of 64 KiB row `row` is fetched; `wants` tells
+// whether this lane has data in that row.  The receiver side uses it to wait until the row has been decoded.
+struct Md5NoGate {
+    __device__ __forceinline__ void operator()(uint64_t, bool) const {}
+};
+
+template <class Gate = Md5NoGate>
 __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uint64_t len, bool active, uint8_t *out,
-                                         unsigned lane, volatile uint32_t *progress) {
+                                         unsigned lane, volatile uint32_t *progress, Gate gate = Gate()) {
     constexpr int kSlots = SKY_MD5_SLOTS;  // ring depth (blocks, power of two); prefetch distance = kSlots - 1
+    constexpr bool kGated = !std::is_same<Gate, Md5NoGate>::value;
     const uint64_t nfull = active ? (len >> 6) : 0;
     uint64_t wmax = nfull;
 #pragma unroll
@@ -150,6 +160,7 @@ __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uin
     // slot s, piece q of this lane lives at ring[((s*4 + q)*32 + lane) * 4 words]
     auto slot_addr = [&](int s, int q) { return ring_base + (uint32_t)(((s * 4 + q) * 32 + lane) * 16); };
 
+    gate(0, active && len > 0);
 #pragma unroll
     for (int s = 0; s < kSlots - 1; s++) {
         if ((uint64_t)s < nfull) {
@@ -174,22 +185,37 @@ __device__ __forceinline__ void md5_warp(uint32_t *ring, const uint8_t *src, uin
     for (int k = 0; k < 16; k++) wn[k] = 0;
     cp_async_wait<kSlots - 2>();  // block 0 has landed
     if (nfull) load_words(wn, 0);
-    for (uint64_t i = 0; i < wmax; i++) {
-        uint32_t w[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) w[k] = wn[k];
-        const uint64_t pf = i + (kSlots - 1);
-        if (pf < nfull) {
-            const int ps = (int)(pf & (kSlots - 1));  // == slot of block i-1, last read one iteration ago
-#pragma unroll
-            for (int q = 0; q < 4; q++) cp_async16(slot_addr(ps, q), src + pf * 64 + q * 16);
-        }
-        cp_async_commit();
-        cp_async_wait<kSlots - 2>();  // block i+1 has landed
-        if (i + 1 < nfull) load_words(wn, (int)((i + 1) & (kSlots - 1)));
-        if (i < nfull) md5_block(st, w);
-        if (progress && lane == 0 && ((i + 1) & 1023) == 0) *progress = (uint32_t)((i + 1) >> 10) + 1u;  // 1 + 64 KiB rows done
+#define SKY_MD5_LOOP_BODY(i)                                                                              \
+    {                                                                                                     \
+        uint32_t w[16];                                                                                   \
+        _Pragma("unroll") for (int k = 0; k < 16; k++) w[k] = wn[k];                                      \
+        const uint64_t pf = (i) + (kSlots - 1);                                                           \
+        if (pf < nfull) {                                                                                 \
+            const int ps = (int)(pf & (kSlots - 1)); /* == slot of block i-1, last read one iteration ago */ \
+            _Pragma("unroll") for (int q = 0; q < 4; q++) cp_async16(slot_addr(ps, q), src + pf * 64 + q * 16); \
+        }                                                                                                 \
+        cp_async_commit();                                                                                \
+        cp_async_wait<kSlots - 2>(); /* block i+1 has landed */                                           \
+        if ((i) + 1 < nfull) load_words(wn, (int)(((i) + 1) & (kSlots - 1)));                             \
+        if ((i) < nfull) md5_block(st, w);                                                                \
     }
+    if constexpr (kGated) {
+        // Receiver side: a row-granular outer loop keeps the gate (a spin with a scheduling barrier) out of the
+        // chain-bound inner loop; the prefetch runs kSlots-1 blocks ahead, so a row is gated one row early.
+        for (uint64_t base = 0; base < wmax; base += 1024) {
+            gate((base >> 10) + 1, (base + 1024) * 64 < len);
+            const uint64_t iend = (wmax - base > 1024) ? base + 1024 : wmax;
+            for (uint64_t i = base; i < iend; i++) SKY_MD5_LOOP_BODY(i)
+        }
+    } else {
+        // Sender side: one flat loop (measured 1.027x faster per block than the nested form); lane 0 publishes the
+        // rows consumed so LZ4 warps can stay just ahead of the digest lanes.
+        for (uint64_t i = 0; i < wmax; i++) {
+            SKY_MD5_LOOP_BODY(i)
+            if (progress && lane == 0 && ((i + 1) & 1023) == 0) *progress = (uint32_t)((i + 1) >> 10) + 1u;  // 1 + 64 KiB rows done
+        }
+    }
+#undef SKY_MD5_LOOP_BODY
     cp_async_wait<0>();
     if (active) {
         // tail: rem bytes + 0x80 + zeros + u64le bit length -> one or two more blocks (slow path, once per chunk)

@@ -242,7 +242,11 @@ struct DecParams {
     int32_t *status;     // per chunk, 0 = ok (mapped host memory)
     uint32_t *done;      // per chunk: leading blocks fully decoded (linked frames wait on it)
     uint32_t *counter;   // work counter
+    uint32_t *blk_done;  // per block: 1 once decoded (gates the MD5 lanes)
+    const uint32_t *md5_order;
+    uint8_t *md5_out;    // null = no digest
     uint32_t n_chunks;
+    uint32_t n_groups;
     uint32_t rows;
 };
 
@@ -256,8 +260,43 @@ __global__ void sky_frame_index_kernel(const DecParams p) {
     p.status[c] = st;
 }
 
+// Gate for the MD5 lanes of the receiver: row `row` of a chunk may be hashed once its block has been decoded.
+struct DecRowGate {
+    const uint32_t *flags;  // this lane's chunk: one word per block, non-zero = decoded (or failed: hash garbage, status says so)
+    __device__ __forceinline__ void operator()(uint64_t row, bool wants) const {
+        unsigned ns = 128;
+        for (;;) {
+            const bool ready = !wants || ld_acquire32(flags + row) != 0;
+            if (__all_sync(kFull, ready)) break;
+            __nanosleep(ns);
+            if (ns < 4096) ns <<= 1;
+        }
+    }
+};
+
+// Persistent: warps 0..3 of a CTA may host an MD5 group (digest of the decoded bytes, following the decode through
+// per-block flags); every other warp (and MD5 warps once their groups are done) decodes blocks.
 __global__ void __launch_bounds__(512, 1) sky_decode_kernel(const DecParams p) {
-    const unsigned lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.md5_out && warp < kMd5WarpsPerCta) {
+        const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
+        for (uint32_t g = warp * gridDim.x + blockIdx.x; g < p.n_groups; g += md5_slots) {
+            const uint32_t c = p.md5_order[g * 32 + lane];
+            const bool active = c != 0xffffffffu;
+            const uint8_t *src = nullptr;
+            uint64_t len = 0;
+            DecRowGate gate{nullptr};
+            if (active) {
+                src = p.chunks[c].out;
+                len = p.chunks[c].raw_len;
+                gate.flags = p.blk_done + p.chunks[c].blk_base;
+            }
+            md5_warp(reinterpret_cast<uint32_t *>(smem + warp * kRingBytes), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16,
+                     lane, nullptr, gate);
+            __syncwarp();
+        }
+    }
     const uint32_t total = p.rows * p.n_chunks;
     for (;;) {
         uint32_t w = 0;
@@ -293,9 +332,10 @@ __global__ void __launch_bounds__(512, 1) sky_decode_kernel(const DecParams p) {
             if (st != kDecOk && lane == 0) atomicMin(p.status + c, st);
         }
         __syncwarp();
-        if (cd.linked && lane == 0) {
+        if (lane == 0) {
             __threadfence();
-            st_release32(p.done + c, j + 1);
+            if (cd.linked) st_release32(p.done + c, j + 1);
+            st_release32(p.blk_done + cd.blk_base + j, 1u);  // lets the MD5 lane of this chunk enter the row
         }
     }
 }
@@ -325,6 +365,7 @@ struct Slot {
     // receiver side
     DecChunk *h_dchunks = nullptr, *d_dchunks = nullptr;
     DecBlock *d_dblocks = nullptr;
+    uint32_t *d_blkdone = nullptr;
     uint64_t dblocks_cap = 0;
     int32_t *h_dstatus = nullptr, *d_dstatus = nullptr;  // pinned host mirror / device array
     // in-flight ticket
@@ -441,7 +482,7 @@ static void free_slot(Slot &s) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
     cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters);
-    cudaFreeHost(s.h_dchunks); cudaFree(s.d_dchunks); cudaFree(s.d_dblocks); cudaFreeHost(s.h_dstatus); cudaFree(s.d_dstatus); cudaFree(s.d_freed); cudaFree(s.d_progress);
+    cudaFreeHost(s.h_dchunks); cudaFree(s.d_dchunks); cudaFree(s.d_dblocks); cudaFree(s.d_blkdone); cudaFreeHost(s.h_dstatus); cudaFree(s.d_dstatus); cudaFree(s.d_freed); cudaFree(s.d_progress);
     cudaFree(s.d_in); cudaFree(s.d_out);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
@@ -777,28 +818,44 @@ static int launch_decode(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, con
     if (nblk_total + 1 > s.dblocks_cap) {
         CK(ctx, cudaStreamSynchronize(st));
         cudaFree(s.d_dblocks);
+        cudaFree(s.d_blkdone);
         s.d_dblocks = nullptr;
+        s.d_blkdone = nullptr;
         s.dblocks_cap = 0;
         CK(ctx, cudaMalloc(&s.d_dblocks, (nblk_total + 1) * sizeof(DecBlock)));
+        CK(ctx, cudaMalloc(&s.d_blkdone, (nblk_total + 1) * sizeof(uint32_t)));
         s.dblocks_cap = nblk_total + 1;
     }
     CK(ctx, cudaMemcpyAsync(s.d_dchunks, s.h_dchunks, n * sizeof(DecChunk), cudaMemcpyHostToDevice, st));
     CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
     CK(ctx, cudaMemsetAsync(s.d_freed, 0, n * sizeof(uint32_t), st));
     CK(ctx, cudaMemsetAsync(s.d_dstatus, 0, n * sizeof(int32_t), st));
+    CK(ctx, cudaMemsetAsync(s.d_blkdone, 0, (nblk_total + 1) * sizeof(uint32_t), st));
+    // MD5 lane assignment: longest chunks first (same rule as the sender side)
+    const uint32_t ng = (n + 31) / 32;
+    std::iota(s.h_order, s.h_order + n, 0u);
+    std::stable_sort(s.h_order, s.h_order + n, [&](uint32_t a, uint32_t b) { return raw_len[a] > raw_len[b]; });
+    for (uint32_t i = n; i < ng * 32; i++) s.h_order[i] = 0xffffffffu;
+    CK(ctx, cudaMemcpyAsync(s.d_order, s.h_order, ng * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    memset(s.h_md5, 0, (size_t)n * 16);
     DecParams p;
     p.chunks = s.d_dchunks;
     p.blocks = s.d_dblocks;
     p.status = s.d_dstatus;
     p.done = s.d_freed;
     p.counter = s.d_counters;
+    p.blk_done = s.d_blkdone;
+    p.md5_order = s.d_order;
+    p.md5_out = s.d_md5;
     p.n_chunks = n;
+    p.n_groups = ng;
     p.rows = rows;
     CK(ctx, cudaEventRecord(s.ev_h0, st));  // start marker of the receiver-side kernels
     sky_frame_index_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
     CK(ctx, cudaGetLastError());
-    sky_decode_kernel<<<ctx->sm_count, 512, 0, st>>>(p);
+    sky_decode_kernel<<<ctx->sm_count, 512, kMd5WarpsPerCta * kRingBytes, st>>>(p);
     CK(ctx, cudaGetLastError());
+    CK(ctx, cudaEventRecord(s.ev_k1, st));
     ctx->launches += 2;
     CK(ctx, cudaMemcpyAsync(s.h_dstatus, s.d_dstatus, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     return SKY_OK;
@@ -819,10 +876,6 @@ int sky_decode_device(sky_ctx *ctx, uint32_t n, const void *d_frames, const uint
     if (s.busy) return SKY_E_BUSY;
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
     int rc = launch_decode(ctx, s, st, n, (const uint8_t *)d_frames, frame_off, frame_len, (uint8_t *)d_out, out_off, raw_len);
-    if (rc != SKY_OK) return rc;
-    // MD5 over the decoded output: same kernel, MD5 role only (src = decoded regions; dst unused)
-    std::vector<uint64_t> dst_off(n, 0);
-    rc = launch_batch(ctx, s, st, st, n, (const uint8_t *)d_out, out_off, raw_len, (uint8_t *)d_out, dst_off.data(), SKY_F_MD5);
     if (rc != SKY_OK) return rc;
     CK(ctx, cudaStreamSynchronize(st));
     if (status) memcpy(status, s.h_dstatus, n * sizeof(int32_t));

@@ -391,3 +391,53 @@ def test_compress_hash_worker_loop_with_stub_stage(tmp_path):
         assert err_ev.is_set() and "max_batch_bytes" in err_q.get(timeout=2)
     finally:
         op.stop_workers()
+
+
+# ------------------------------------------------------------------ wire framing from staging buffers
+def test_wire_send_recv_roundtrip(golden):
+    import threading
+
+    import oracle
+    from skyplane_b200 import wire
+    from skyplane_b200.stage import StageResult
+
+    datas = [os.urandom(70000), b"hello " * 5000, b""]
+    chunks = [Chunk("k", "k", ("%02x" % (i + 1)) * 16, len(d)) for i, d in enumerate(datas)]
+    results = []
+    for d in datas:
+        f = oracle.lz4f_compress_indep(d)
+        results.append(StageResult(frame=memoryview(bytearray(f)), md5=b"\0" * 16, raw_len=len(d), comp_len=len(f)))
+    a, b = socket.socketpair()
+    try:
+        t = threading.Thread(target=wire.send_results, args=(a, chunks, results))
+        t.start()
+        buf = bytearray(1 << 20)
+        for i, (c, d, r) in enumerate(zip(chunks, datas, results)):
+            hdr, n = wire.recv_chunk(b, buf)
+            assert hdr.chunk_id == c.chunk_id and hdr.data_len == r.comp_len == n and hdr.raw_data_len == len(d)
+            assert hdr.is_compressed and hdr.n_chunks_left_on_socket == len(chunks) - i - 1
+            assert oracle.lz4f_decode(bytes(buf[:n]), len(d)) == d
+        t.join()
+        # byte-level: what goes on the wire starts with exactly the reference's header bytes
+        case = golden["wire_headers"]["headers"][1]
+        c = Chunk("s", "d", case["fields"]["chunk_id"], case["fields"]["raw_data_len"])
+        payload = bytes(case["fields"]["data_len"])
+        ta = threading.Thread(target=wire.send_chunk, args=(a, c, payload, case["fields"]["raw_data_len"]))
+        ta.start()
+        raw = bytearray()
+        want = 53 + len(payload)
+        while len(raw) < want:
+            raw += b.recv(want - len(raw))
+        ta.join()
+        assert raw[:53].hex() == case["bytes_hex"]
+        with pytest.raises(ValueError):
+            tb = threading.Thread(target=wire.send_chunk, args=(a, c, b"x" * 100, 100))
+            tb.start()
+            try:
+                wire.recv_chunk(b, bytearray(10))
+            finally:
+                b.recv(200)
+                tb.join()
+    finally:
+        a.close()
+        b.close()
