@@ -510,6 +510,8 @@ int sky_ctx_create(int device, uint64_t max_batch_bytes, uint32_t max_chunks, ui
     auto fail = [&](int rc) {
         g_err = ctx->err;
         for (auto &s : ctx->slots) free_slot(s);
+        if (ctx->st_h2d) cudaStreamDestroy(ctx->st_h2d);
+        if (ctx->st_d2h) cudaStreamDestroy(ctx->st_d2h);
         delete ctx;
         return rc;
     };

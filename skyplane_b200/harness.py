@@ -151,7 +151,9 @@ def main():
     base = Path(a.dir or tempfile.mkdtemp(prefix="skyb200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
     pool_dir = base / "pool"
     pool_dir.mkdir(parents=True, exist_ok=True)
-    files, lens = [], []
+    import hashlib
+
+    files, lens, digests = [], [], []
     for k in range(a.pool):
         kind = a.workload if a.workload != "mixed" else ("random" if k % 2 else "silesia")
         data = synth.random_chunk(3000 + k, n) if kind == "random" else synth.silesia_like_chunk(3000 + k, n)
@@ -159,14 +161,18 @@ def main():
         p.write_bytes(data)
         files.append(p)
         lens.append(n)
+        digests.append(hashlib.md5(data).hexdigest())  # hashlib = the reference's own call (s3_interface.py:181)
     try:
         warm = a.warmup if a.warmup >= 0 else 4 * a.batch * a.gpus
         res = run_stream(base / "chunks", files, lens, a.chunks + warm, n_workers=a.gpus, n_gpus=a.gpus, max_batch_chunks=a.batch,
                          max_batch_bytes=max(n * a.batch, 64 << 20), keep_frames=False, window=max(256, 4 * a.batch * a.gpus),
                          warmup_requests=warm)
+        bad = [r["chunk_id"] for r in res["records"] if r["md5"] != digests[r["pool_index"]]]
+        if bad:
+            raise SystemExit(f"{len(bad)} chunks came back with a wrong MD5, e.g. {bad[:3]}")
         gbs = res["bytes"] / res["wall_s"] / 1e9
         print(json.dumps({"metric": "gateway-queue end-to-end GB/s (raw input)", "value": gbs, "n_gpus": a.gpus, "chunks": a.chunks,
-                          "chunk_mib": a.chunk_mib, "wall_s": res["wall_s"], "status": res["status"],
+                          "chunk_mib": a.chunk_mib, "wall_s": res["wall_s"], "status": res["status"], "md5_verified": len(res["records"]),
                           "ratio": (res["uncompressed_bytes"] / res["compressed_bytes"]) if res["compressed_bytes"] else None}))
     finally:
         shutil.rmtree(base, ignore_errors=True)
