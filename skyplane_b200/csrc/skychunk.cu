@@ -122,10 +122,14 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
         if (pace) {
             // stay at most one 64 KiB row ahead of the MD5 lanes of this chunk (only while they are running)
             const uint32_t *pw = p.md5_progress + cd.group;
+            // the last rows of a chunk may run up to kTailLead rows ahead, so the compressor's own latency for the
+            // final row (milliseconds on compressible data) overlaps the digest's last rows instead of trailing them
+            constexpr uint32_t kTailLead = 8;
+            const uint32_t lead = (cd.nblk - j <= kTailLead) ? kTailLead : 0;
             unsigned ns = 64;
             for (;;) {
                 const uint32_t pr = ld_relaxed32(pw);
-                if (pr == 0 || j + 1 <= pr) break;  // pr - 1 rows consumed: rows <= pr allowed
+                if (pr == 0 || j + 1 <= pr + lead) break;  // pr - 1 rows consumed: rows <= pr (+ lead) allowed
                 __nanosleep(ns);
                 if (ns < 4096) ns <<= 1;
             }
