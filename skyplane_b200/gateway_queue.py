@@ -1,83 +1,94 @@
-"""Queues that connect gateway operators (mirror of skyplane/gateway/gateway_queue.py:4-61).
+"""Inter-operator queues of the gateway (API-compatible with skyplane/gateway/gateway_queue.py:4-61).
 
-``GatewayQueue`` wraps one bounded ``multiprocessing.Queue``; ``GatewayANDQueue`` fans every item
-out to one private queue per registered operator handle.  Kept API-compatible so the B200 operator
-can sit in a stock ``gateway_daemon`` operator graph.  ``get_batch_nowait`` is an addition used by
-the batch-draining worker loop.
+* ``GatewayQueue``    -- one bounded multiprocessing queue shared by the workers of the consuming operator.
+* ``GatewayANDQueue`` -- fan-out: every registered consumer handle gets its own ``GatewayQueue`` and sees every item.
+
+``get_batch_nowait`` is ours: the B200 operator drains many requests per kernel launch.
 """
 from __future__ import annotations
 
-import queue
-from multiprocessing import Queue
-from typing import Dict, List
+import multiprocessing
+import queue as _queue
+from typing import Dict, Iterable, List
+
+DEFAULT_DEPTH = 10000  # the reference's maxsize
 
 
 class GatewayQueue:
-    def __init__(self, maxsize: int = 10000):
-        self.q = Queue(maxsize)
+    """FIFO of ChunkRequests between two operators."""
+
+    def __init__(self, maxsize: int = DEFAULT_DEPTH):
+        self.q = multiprocessing.Queue(maxsize)
         self.handles: List[str] = []
 
-    def register_handle(self, requester_handle):
+    # -- consumers ------------------------------------------------------------------------------
+    def register_handle(self, requester_handle) -> None:
         self.handles.append(requester_handle)
 
-    def get_handles(self):
+    def get_handles(self) -> List[str]:
         return self.handles
 
-    def put(self, chunk_req):
-        self.q.put(chunk_req)
-
-    def put_nowait(self, chunk_req):
-        self.q.put_nowait(chunk_req)
-
-    def pop(self, requester_handle=None):
-        self.q.get()
-
     def get_nowait(self, requester_handle=None):
-        return self.q.get_nowait()  # raises queue.Empty
+        """Next request or ``queue.Empty``."""
+        return self.q.get_nowait()
 
     def get_batch_nowait(self, max_items: int, requester_handle=None) -> list:
-        """Drain up to ``max_items`` without blocking (may return [])."""
-        out = []
-        try:
-            while len(out) < max_items:
-                out.append(self.get_nowait(requester_handle))
-        except queue.Empty:
-            pass
-        return out
+        """Up to ``max_items`` requests that are available right now (possibly none)."""
+        batch: list = []
+        while len(batch) < max_items:
+            try:
+                batch.append(self.get_nowait(requester_handle))
+            except _queue.Empty:
+                break
+        return batch
 
-    def size(self):
+    def pop(self, requester_handle=None) -> None:
+        self.q.get()
+
+    # -- producers ------------------------------------------------------------------------------
+    def put(self, chunk_req) -> None:
+        self.q.put(chunk_req)
+
+    def put_nowait(self, chunk_req) -> None:
+        self.q.put_nowait(chunk_req)
+
+    def put_many(self, chunk_reqs: Iterable) -> None:
+        for r in chunk_reqs:
+            self.q.put(r)
+
+    def size(self) -> int:
         return self.q.qsize()
 
 
 class GatewayANDQueue(GatewayQueue):
-    """Every downstream operator sees every chunk: one GatewayQueue per handle."""
+    """Broadcast queue: ``put`` delivers to every consumer's private queue (used behind ``mux_and``)."""
 
-    def __init__(self, maxsize: int = 10000):
-        self.q: Dict[str, GatewayQueue] = {}
+    def __init__(self, maxsize: int = DEFAULT_DEPTH):
         self.maxsize = maxsize
-        self.temp_q = Queue(maxsize)
+        self.q: Dict[str, GatewayQueue] = {}  # handle -> private queue
+        self.temp_q = multiprocessing.Queue(maxsize)
 
-    def register_handle(self, requester_handle):
+    def register_handle(self, requester_handle) -> None:
         self.q[requester_handle] = GatewayQueue(self.maxsize)
 
-    def get_handles(self):
-        return list(self.q.keys())
+    def get_handles(self) -> List[str]:
+        return list(self.q)
 
-    def get_handle_queue(self, requester_handle):
+    def get_handle_queue(self, requester_handle) -> GatewayQueue:
         return self.q[requester_handle]
-
-    def put(self, chunk_req):
-        for sub in self.q.values():
-            sub.put(chunk_req)
-
-    def put_nowait(self, chunk_req):
-        raise ValueError("GatewayANDQueue cannot be the first queue in a pipeline")
-
-    def pop(self, requester_handle):
-        self.q[requester_handle].pop()
 
     def get_nowait(self, requester_handle):
         return self.q[requester_handle].get_nowait()
 
-    def size(self):
-        return max((sub.size() for sub in self.q.values()), default=0)
+    def pop(self, requester_handle) -> None:
+        self.q[requester_handle].pop()
+
+    def put(self, chunk_req) -> None:
+        for private in self.q.values():
+            private.put(chunk_req)
+
+    def put_nowait(self, chunk_req) -> None:
+        raise ValueError("GatewayANDQueue cannot be the first queue in a pipeline")
+
+    def size(self) -> int:
+        return max((private.size() for private in self.q.values()), default=0)

@@ -161,3 +161,59 @@ def test_chunk_stage_pair():
     frame, digest = oracle.chunk_stage(data)
     assert digest == hashlib.md5(data).digest()
     assert oracle.lz4f_decode(frame, len(data)) == data
+
+
+# ---------------------------------------------------------------- property tests (hypothesis): structured random inputs
+def _structured(draw_bytes, rng_seed, n_segments):
+    """Concatenation of segments: random bytes, runs, repeats of earlier content, ascii words."""
+    r = np.random.default_rng(rng_seed)
+    out = bytearray()
+    for _ in range(n_segments):
+        kind = int(r.integers(0, 5))
+        ln = int(r.integers(1, 3000))
+        if kind == 0:
+            out += r.bytes(ln)
+        elif kind == 1:
+            out += bytes([int(r.integers(0, 256))]) * ln
+        elif kind == 2 and len(out) > 8:
+            start = int(r.integers(0, len(out) - 4))
+            seg = bytes(out[start : start + min(ln, len(out) - start)])
+            out += seg * int(r.integers(1, 4))
+        elif kind == 3:
+            out += (b"alpha beta gamma delta " * (ln // 23 + 1))[:ln]
+        else:
+            per = int(r.integers(1, 40))
+            out += (r.bytes(per) * (ln // per + 1))[:ln]
+    return bytes(out)
+
+
+try:
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @pytest.mark.skipif(not ref.available(), reason="liblz4.so.1 not present")
+    @settings(max_examples=120, deadline=None)
+    @given(seed=st.integers(0, 2**32 - 1), nseg=st.integers(0, 60), pad=st.integers(0, 70000))
+    def test_property_compressor_byte_identical_to_liblz4(seed, nseg, pad):
+        data = _structured(None, seed, nseg) + bytes(pad % 7) + np.random.default_rng(seed ^ 1).bytes(pad if seed % 3 == 0 else 0)
+        frame = oracle.lz4f_compress(data)
+        assert frame == ref.lz4f_compress(data)
+        assert oracle.lz4f_decode(frame, len(data)) == data
+        indep = oracle.lz4f_compress_indep(data)
+        assert oracle.lz4f_decode(indep, len(data)) == data == ref.lz4f_decompress(indep, len(data))
+        assert oracle.md5(data) == hashlib.md5(data).digest()
+
+    @settings(max_examples=200, deadline=None)
+    @given(blob=st.binary(min_size=0, max_size=400), raw=st.integers(0, 5000))
+    def test_property_decoder_never_crashes_on_garbage(blob, raw):
+        """Arbitrary bytes either decode (and then liblz4 agrees) or raise OracleError -- no crash, no overrun."""
+        hdr = bytes.fromhex("04224d186040") + bytes([(oracle.xxh32(bytes([0x60, 0x40])) >> 8) & 0xFF])
+        frame = hdr + blob
+        try:
+            out = oracle.lz4f_decode(frame, raw)
+        except oracle.OracleError:
+            return
+        if ref.available():
+            assert ref.lz4f_decompress(frame[: len(frame)], max(raw, 1))[: len(out)] == out
+except ImportError:  # hypothesis not installed: the parametrised differential tests above still run
+    pass
