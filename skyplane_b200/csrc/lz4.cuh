@@ -233,8 +233,14 @@ __device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src,
     }
 }
 
-constexpr int kExtRounds = 7;        // per-lane extension: up to 4 + 4*7 = 32 bytes before going cooperative
-constexpr uint32_t kCoopLit = 48;    // literal runs at least this long are copied by the whole warp
+#ifndef SKY_EXT_ROUNDS
+#define SKY_EXT_ROUNDS 7
+#endif
+#ifndef SKY_COOP_LIT
+#define SKY_COOP_LIT 48
+#endif
+constexpr int kExtRounds = SKY_EXT_ROUNDS;     // per-lane extension: up to 4 + 4*rounds bytes before going cooperative
+constexpr uint32_t kCoopLit = SKY_COOP_LIT;    // literal runs at least this long are copied by the whole warp
 
 // ---- the block compressor -------------------------------------------------------------------------
 // src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: where compressed
@@ -274,21 +280,26 @@ __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict
                 cand = ht[h];
             }
             bool hit = valid && cand < pos && load32(src, cand) == v;
-            // The table only knows positions before this window.  A nearer occurrence inside the window (offsets
-            // below 32*step: runs, short periods, repeated words) is found by matching the 4-byte values across
-            // lanes; like the sequential reference, the most recent occurrence wins.
+            // Lanes that hash to the same slot are grouped with one match.any: (a) the nearest lower lane of the
+            // group is the most recent occurrence inside the window (offsets below 32*step: runs, short periods,
+            // repeated words), which the table cannot know yet -- like the sequential reference, the most recent
+            // occurrence wins; (b) only the highest lane of a group stores its position, so the table update is
+            // deterministic and free of same-instruction write-write conflicts.
+            const unsigned vmask = __ballot_sync(kFull, valid);
+            const unsigned grp = __match_any_sync(kFull, valid ? h : (0xffff0000u | lane)) & vmask;
             {
-                const unsigned vmask = __ballot_sync(kFull, valid);
-                const unsigned same = __match_any_sync(kFull, valid ? v : (0x9e3779b9u ^ lane)) & vmask & lt_mask;
-                if (valid && same) {
-                    cand = ip + (uint32_t)(31 - __clz(same)) * step;
+                const unsigned lower = grp & lt_mask;
+                const int near = lower ? 31 - __clz(lower) : 0;
+                const uint32_t v_near = __shfl_sync(kFull, v, near);
+                if (valid && lower && v_near == v) {
+                    cand = ip + (uint32_t)near * step;
                     hit = true;
                 }
             }
             const unsigned hits = __ballot_sync(kFull, hit);  // (also orders the table reads before the writes)
             // every probed position enters the table: the cursor always moves past the whole window, so no
             // entry can point ahead of a later probe
-            if (valid) ht[h] = (uint16_t)pos;
+            if (valid && (grp >> lane) == 1u) ht[h] = (uint16_t)pos;
             __syncwarp();
             if (hits == 0) {
                 ip += 32 * step;

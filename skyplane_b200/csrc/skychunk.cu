@@ -129,7 +129,9 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
             unsigned ns = 64;
             for (;;) {
                 const uint32_t pr = ld_relaxed32(pw);
-                if (pr == 0 || j + 1 <= pr + lead) break;  // pr - 1 rows consumed: rows <= pr (+ lead) allowed
+                // pr: 0 = digest not started, 0xffffffff = digest finished, else 1 + rows consumed (64-bit compare:
+                // pr + lead must not wrap when the digest has already finished)
+                if (pr == 0 || (uint64_t)j + 1 <= (uint64_t)pr + lead) break;
                 __nanosleep(ns);
                 if (ns < 4096) ns <<= 1;
             }

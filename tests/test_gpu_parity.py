@@ -164,6 +164,20 @@ def test_batch_of_8mib_chunks(ctx):
     assert hashlib.md5(b"".join(digests)).digest() == hashlib.md5(b"".join(hashlib.md5(d).digest() for d in datas)).digest()
 
 
+@pytest.mark.timeout(120)
+def test_compressor_slower_than_digest_with_many_rows(ctx):
+    """Many compressible multi-row chunks: the MD5 lanes finish long before the LZ4 warps, so the tail rows are
+    released against a 'digest finished' progress word (regression: that comparison once wrapped and hung)."""
+    base = [synth.silesia_like_chunk(70 + i, 12 * 65536 + 4321 * i) for i in range(6)]
+    datas = [base[i % 6] for i in range(420)]
+    frames, digests, lens, _ = run_device(ctx, datas)
+    want = [hashlib.md5(d).digest() for d in base]
+    assert digests == [want[i % 6] for i in range(420)]
+    for i in (0, 1, 2, 3, 4, 5, 417, 419):
+        check_frame(frames[i], datas[i])
+    assert all(frames[i] == frames[i % 6] for i in range(420))  # same input -> same frame, whatever warp did it
+
+
 def test_run_to_run_determinism(ctx):
     datas = [synth.silesia_like_chunk(9, 3 << 20), kinds(200000)["half"]]
     a = run_device(ctx, datas)[0]
