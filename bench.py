@@ -341,7 +341,7 @@ def run_gpu(args):
         n_sub = (n_chunks + sub - 1) // sub
         slots = args.e2e_slots
         ectx = native.Context(local, sub * stride_in, sub, slots)
-        pool_n = min(64, n_chunks)
+        pool_n = min(64 if args.workload == "random" else 16, n_chunks)  # distinct host chunks, recycled
         pin_in = native.PinnedBuffer(pool_n * stride_in)
         if args.workload == "random":
             for i in range(pool_n):

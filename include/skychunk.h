@@ -103,8 +103,9 @@ SKY_API int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, cons
  * (WireProtocolHeader.raw_data_len, skyplane/chunk.py:100).  Accepts the frames this library emits (independent
  * 64 KiB blocks) and the reference sender's (linked blocks); status[i] = 0 or a SKY_D_* code (a bad frame is an
  * error status, never a crash); md5[16*i..] = MD5 of the decoded bytes.
- * sky_decode_device: frames and output already in HBM (out_off multiples of 16).  sky_decode: host buffers,
- * synchronous, through slot 0's slabs (needs n_slots >= 1). */
+ * sky_decode_device: frames and output already in HBM (out_off multiples of 16; each frame region must be readable
+ * up to the next multiple of 4 bytes, each output region writable up to the next multiple of 16).  sky_decode: host
+ * buffers, synchronous, through slot 0's slabs (needs n_slots >= 1). */
 #define SKY_D_OK 0
 #define SKY_D_BAD_HEADER (-1)
 #define SKY_D_CORRUPT (-2)
