@@ -18,7 +18,7 @@ from skyplane_b200.gateway_queue import GatewayQueue
 from skyplane_b200.operators import ChecksumMismatchException, GatewayCompressHash, GatewayDecompressVerify
 from skyplane_b200.stage import ChunkStage
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 RNG = np.random.default_rng(99)
 LENS = [0, 1, 12, 13, 100, 4096, 65535, 65536, 65537, 131073, 200000, (1 << 20) + 5]
 

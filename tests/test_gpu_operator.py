@@ -15,7 +15,7 @@ import oracle.reflib as ref
 from skyplane_b200 import synth
 from skyplane_b200.chunk import WireProtocolHeader
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 ROOT = Path(__file__).resolve().parent.parent
 
 DRIVER = r"""

@@ -16,7 +16,7 @@ from gpu_util import run_device
 from skyplane_b200 import native, synth
 from skyplane_b200.stage import ChunkStage
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
 RNG = np.random.default_rng(77)
 EDGE_LENS = [0, 1, 2, 11, 12, 13, 14, 15, 16, 17, 55, 56, 63, 64, 65, 119, 120, 128, 255, 4096, 65535, 65536, 65537,
