@@ -164,7 +164,7 @@ def test_batch_of_8mib_chunks(ctx):
     assert hashlib.md5(b"".join(digests)).digest() == hashlib.md5(b"".join(hashlib.md5(d).digest() for d in datas)).digest()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(120, method="thread")
 def test_compressor_slower_than_digest_with_many_rows(ctx):
     """Many compressible multi-row chunks: the MD5 lanes finish long before the LZ4 warps, so the tail rows are
     released against a 'digest finished' progress word (regression: that comparison once wrapped and hung)."""
