@@ -441,3 +441,67 @@ def test_wire_send_recv_roundtrip(golden):
     finally:
         a.close()
         b.close()
+
+
+# ------------------------------------------------------------------ gateway-program loader (reference JSON schema)
+class _Sink(GatewayOperator):
+    """Terminal stand-in for send / write_object_store: records what it saw in a file."""
+
+    def process(self, chunk_req, *args):
+        with open(self.chunk_store.chunk_dir / f"{self.handle}.seen", "a") as f:
+            f.write(chunk_req.chunk.chunk_id + " " + (chunk_req.chunk.md5_hash or b"").hex() + "\n")
+        return True
+
+
+def test_program_loader_wires_reference_schema(tmp_path):
+    import hashlib
+
+    from skyplane_b200.program import build_operator_graph
+
+    program = [{
+        "partitions": ["0", "1"],
+        "value": [{
+            "op_type": "compress_hash", "handle": "a", "num_gpus": 1, "compress": True,
+            "children": [{"op_type": "mux_and", "handle": "b", "children": [
+                {"op_type": "mux_or", "handle": "c", "children": [{"op_type": "send", "handle": "d", "children": []},
+                                                                 {"op_type": "send", "handle": "e", "children": []}]},
+                {"op_type": "write_local", "handle": "f", "children": []},
+            ]}],
+        }],
+    }]
+    cs = ChunkStore(tmp_path)
+    ev, eq = mp.Event(), mp.Queue()
+    sink = lambda op, kw: _Sink(**kw, n_processes=1)
+    factories = {"send": sink, "write_local": sink,
+                 "compress_hash": lambda op, kw: _StubbedCompressHash(**kw, n_processes=op["num_gpus"], max_batch_chunks=4, read_threads=1)}
+    g = build_operator_graph(program, cs, "test:r", ev, eq, factories)
+    assert set(g.operators) == {"compress_hash_a", "send_d", "send_e", "write_local_f"}
+    assert g.num_required_terminal == {"0": 2, "1": 2}  # one branch through the mux_or, one through write_local
+    assert sorted(g.terminal_operators["0"]) == ["send_d", "send_e", "write_local_f"] and g.n_processes == 4
+    comp = g.operators["compress_hash_a"]
+    assert isinstance(comp.output_queue, GatewayANDQueue) and sorted(comp.output_queue.get_handles()) == ["mux_or_c", "write_local_f"]
+    assert g.operators["send_d"].input_queue is g.operators["send_e"].input_queue  # mux_or: either sender takes the chunk
+    assert cs.chunk_requests["0"] is cs.chunk_requests["1"] is comp.input_queue
+    with pytest.raises(ValueError, match="Unsupported op_type"):
+        build_operator_graph([{"partitions": ["9"], "value": [{"op_type": "teleport", "handle": "x", "children": []}]}],
+                             ChunkStore(tmp_path / "other"), "r", ev, eq)
+    # run it: one chunk must reach write_local_f and exactly one of the two senders, with the digest attached
+    data = b"program loader " * 4000
+    cid = "5a" * 16
+    cs.get_chunk_file_path(cid).write_bytes(data)
+    g.start()
+    try:
+        cs.add_chunk_request(ChunkRequest(Chunk("k", "k", cid, len(data), partition_id="0")))
+        t0 = time.time()
+        seen = {}
+        while time.time() - t0 < 20:
+            seen = {h: (cs.chunk_dir / f"{h}.seen").read_text().split() for h in ("send_d", "send_e", "write_local_f")
+                    if (cs.chunk_dir / f"{h}.seen").exists()}
+            if "write_local_f" in seen and ("send_d" in seen or "send_e" in seen):
+                break
+            time.sleep(0.05)
+        assert seen["write_local_f"] == [cid, hashlib.md5(data).hexdigest()]
+        assert ("send_d" in seen) != ("send_e" in seen)
+        assert not ev.is_set()
+    finally:
+        g.stop()
