@@ -164,6 +164,19 @@ def test_batch_of_8mib_chunks(ctx):
     assert hashlib.md5(b"".join(digests)).digest() == hashlib.md5(b"".join(hashlib.md5(d).digest() for d in datas)).digest()
 
 
+def test_multipart_sized_chunks(ctx):
+    """64 MiB is the reference's multipart part size (skyplane/api/config.py:115-118): 1024 block rows per chunk,
+    frame offsets beyond 2^26, ragged companions in the same launch."""
+    big = synth.silesia_like_chunk(80, 16 << 20) * 4  # 64 MiB, compressible
+    odd = synth.random_chunk(81, (33 << 20) + 12345)  # 33 MiB + change, incompressible
+    datas = [big, odd, b"tail" * 1000]
+    frames, digests, lens, _ = run_device(ctx, datas)
+    for d, f, dg in zip(datas, frames, digests):
+        info = check_frame(f, d)
+        assert dg == hashlib.md5(d).digest()
+    assert len(frames[1]) == native.frame_bound(len(odd)) and len(frames[0]) < len(big) * 0.6
+
+
 @pytest.mark.timeout(120, method="thread")
 def test_compressor_slower_than_digest_with_many_rows(ctx):
     """Many compressible multi-row chunks: the MD5 lanes finish long before the LZ4 warps, so the tail rows are
