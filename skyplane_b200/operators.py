@@ -129,6 +129,7 @@ class GatewayCompressHash(GatewayOperator):
         n_gpus: Optional[int] = None,
         keep_frames_on_disk: bool = True,
         read_threads: int = 8,
+        ingest_read_local: bool = True,
     ):
         super().__init__(handle, region, input_queue, output_queue, error_event, error_queue, chunk_store, n_processes)
         self.use_compression = use_compression
@@ -137,6 +138,7 @@ class GatewayCompressHash(GatewayOperator):
         self.n_gpus = n_gpus
         self.keep_frames_on_disk = keep_frames_on_disk
         self.read_threads = read_threads
+        self.ingest_read_local = ingest_read_local
         self._stage = None  # created lazily in the worker process (fork + CUDA)
         self._readers = None  # thread pool for chunk-file reads, also per process
 
@@ -170,19 +172,40 @@ class GatewayCompressHash(GatewayOperator):
         return self.process_batch([chunk_req])[0]
 
     # -- batch plumbing -------------------------------------------------------------------------
-    def _read_into(self, path, view, n: int) -> bool:
-        """Read exactly n bytes of a chunk file into pinned memory; False if the file is not complete yet."""
+    def _read_into(self, path, view, n: int, offset: Optional[int] = None) -> bool:
+        """Read exactly n bytes into pinned memory.  offset None: `path` is a chunk file that must hold exactly n
+        bytes (False if it is not complete yet); otherwise the byte range [offset, offset+n) of a source object."""
         try:
             with open(path, "rb", buffering=0) as f:
+                if offset:
+                    f.seek(offset)
                 got = 0
                 while got < n:
                     r = f.readinto(view[got:])
                     if not r:
                         return False
                     got += r
-                return not f.read(1)
+                return True if offset is not None else not f.read(1)
         except FileNotFoundError:
             return False
+
+    def _source_of(self, chunk_req: ChunkRequest):
+        """-> (path, offset or None, ready).  ``src_type == "read_local"`` (skyplane/chunk.py:54) ingests the byte range
+        straight from the source file into the staging slot -- no tmpfs chunk file in between (SURVEY.md section 8f
+        row 3 for the POSIX case); every other request reads ``<chunk_id>.chunk`` as GatewaySender does."""
+        chunk = chunk_req.chunk
+        n = chunk.chunk_length_bytes
+        if self.ingest_read_local and chunk_req.src_type == "read_local":
+            off = chunk.file_offset_bytes or 0
+            try:
+                return chunk.src_key, off, os.stat(chunk.src_key).st_size >= off + n
+            except FileNotFoundError:
+                return chunk.src_key, off, False
+        path = self.chunk_store.get_chunk_file_path(chunk.chunk_id)
+        try:
+            return path, None, os.stat(path).st_size == n  # upstream writes the file before queueing (gateway_operator.py:567-570)
+        except FileNotFoundError:
+            return path, None, False
 
     def _launch(self, reqs: List[ChunkRequest]):
         """Stage as many of `reqs` as fit one slot and launch them.
@@ -196,24 +219,20 @@ class GatewayCompressHash(GatewayOperator):
             if n > stage.max_batch_bytes:
                 stage.release(slot)
                 raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds the stage's max_batch_bytes")
-            path = self.chunk_store.get_chunk_file_path(chunk.chunk_id)
-            try:
-                ready = os.stat(path).st_size == n  # upstream writes the file before queueing (gateway_operator.py:567-570)
-            except FileNotFoundError:
-                ready = False
+            path, offset, ready = self._source_of(r)
             if not ready:
                 not_ready.append(i)
             elif not stage.fits(slot, n):
                 leftover.append(i)
             else:
-                jobs.append((i, path, slot.reserve(n), n))
+                jobs.append((i, path, slot.reserve(n), n, offset))
         if jobs:
             # file -> pinned memory copies release the GIL: read the batch with a few threads
             if self._readers is None:
                 from concurrent.futures import ThreadPoolExecutor
 
                 self._readers = ThreadPoolExecutor(max_workers=self.read_threads)
-            oks = list(self._readers.map(lambda j: self._read_into(j[1], j[2], j[3]), jobs))
+            oks = list(self._readers.map(lambda j: self._read_into(j[1], j[2], j[3], j[4]), jobs))
             if not all(oks):  # a file changed under us: retry the whole batch later rather than hash partial data
                 stage.release(slot)
                 return None, [], [j[0] for j in jobs] + not_ready, leftover

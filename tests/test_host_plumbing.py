@@ -505,3 +505,32 @@ def test_program_loader_wires_reference_schema(tmp_path):
         assert not ev.is_set()
     finally:
         g.stop()
+
+
+def test_read_local_ingest_skips_the_chunk_file(tmp_path):
+    """src_type == "read_local": the byte range of the source object goes straight into the staging slot."""
+    import hashlib
+
+    import oracle
+
+    cs = ChunkStore(tmp_path / "chunks")
+    ev, eq = mp.Event(), mp.Queue()
+    op = _StubbedCompressHash("ch", "r", GatewayQueue(), None, ev, eq, cs, max_batch_chunks=4, read_threads=2)
+    op.worker_id = 0
+    obj = tmp_path / "object.bin"
+    blob = os.urandom(3000) + b"range " * 3000 + os.urandom(500)
+    obj.write_bytes(blob)
+    try:
+        reqs = [ChunkRequest(Chunk(str(obj), "dst", ("%02x" % (i + 1)) * 16, ln, file_offset_bytes=off, multi_part=True, part_number=i + 1),
+                             src_type="read_local") for i, (off, ln) in enumerate([(0, 3000), (3000, 18000), (21000, 500), (100, 0)])]
+        late = ChunkRequest(Chunk(str(tmp_path / "missing.bin"), "dst", "ee" * 16, 10, file_offset_bytes=0), src_type="read_local")
+        oks = op.process_batch(reqs + [late])
+        assert oks == [True, True, True, True, False]  # a source that is not there yet -> retry, like a missing chunk file
+        for r in reqs:
+            off, ln = r.chunk.file_offset_bytes, r.chunk.chunk_length_bytes
+            assert r.chunk.md5_hash == hashlib.md5(blob[off : off + ln]).digest()
+            frame = cs.get_compressed_file_path(r.chunk.chunk_id).read_bytes()
+            assert oracle.lz4f_decode(frame, ln) == blob[off : off + ln]
+            assert not cs.get_chunk_file_path(r.chunk.chunk_id).exists()  # no tmpfs round trip
+    finally:
+        op.worker_exit(0)
