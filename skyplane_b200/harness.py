@@ -53,6 +53,7 @@ def run_stream(
     timeout_s: float = 600.0,
     on_done: Optional[Callable[[ChunkRequest], None]] = None,
     warmup_requests: int = 0,
+    operator_cls=GatewayCompressHash,
 ) -> Dict:
     """Stream ``n_requests`` chunk requests (recycling ``pool_files`` by hard link) through the operator.
 
@@ -64,7 +65,7 @@ def run_stream(
     qin, qout = GatewayQueue(), GatewayQueue()
     store.add_partition("0", qin)
     err_ev, err_q = mp.Event(), mp.Queue()
-    op = GatewayCompressHash(
+    op = operator_cls(
         "compress_hash", "local:box", qin, qout, err_ev, err_q, store, n_processes=n_workers,
         max_batch_chunks=max_batch_chunks, max_batch_bytes=max_batch_bytes, n_gpus=n_gpus, keep_frames_on_disk=keep_frames,
     )
