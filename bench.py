@@ -36,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 METRIC = "chunk-pipeline GB/s (raw input)"
 UNIT = "GB/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+MD5_FLOOR_GBS_AT_1965 = 64 * 1.965e9 / (64 * 16.28) / 1e9  # 0.1207 GB/s per chain: 64 B per 64 steps x 16.28 cycles
 
 
 # ============================================================================ CPU reference leg
@@ -322,7 +323,12 @@ def run_gpu(args):
         # secondary bound: one MD5 chain per chunk; chain time = 64-byte blocks x cycles/block
         "md5_chain": {"streams": n_chunks, "bytes_per_stream": chunk_bytes,
                       "per_stream_gbs": chunk_bytes / (k_ms * 1e-3) / 1e9,
-                      "note": "kernel time >= one chunk's serial MD5 chain; per_stream_gbs is the achieved single-chain rate"},
+                      # floor measured by tools/md5_chain_bench.cu (profiles/r1_md5_chain_microbench.txt): 16.28 cycles per
+                      # MD5 step x 64 steps per 64-byte block, scaled to the SM clock seen during this run
+                      "per_stream_floor_gbs": MD5_FLOOR_GBS_AT_1965 * ((clocks.get("sm_mhz") or 1965.0) / 1965.0),
+                      "bound_gbs": n_chunks * MD5_FLOOR_GBS_AT_1965 * ((clocks.get("sm_mhz") or 1965.0) / 1965.0),
+                      "frac_of_bound": (total_in / (k_ms * 1e-3) / 1e9) / (n_chunks * MD5_FLOOR_GBS_AT_1965 * ((clocks.get("sm_mhz") or 1965.0) / 1965.0)),
+                      "note": "kernel time >= one chunk's serial MD5 chain; the batch cannot exceed streams x per_stream_floor_gbs"},
     }
     prof = ROOT / "profiles" / "traffic_latest.json"
     if prof.exists():
