@@ -52,6 +52,10 @@ def lib() -> ctypes.CDLL:
             f.restype = ctypes.c_int64
         L.sky_oracle_chunk_stage.argtypes = [u8p, u64, u8p, u64, u8p]
         L.sky_oracle_chunk_stage.restype = ctypes.c_int64
+        L.sky_oracle_secretbox_seal.argtypes = [u8p, u8p, u8p, u64, u8p]
+        L.sky_oracle_secretbox_seal.restype = None
+        L.sky_oracle_secretbox_open.argtypes = [u8p, u8p, u8p, u64, u8p]
+        L.sky_oracle_secretbox_open.restype = ctypes.c_int
         L.sky_oracle_strerror.argtypes = [ctypes.c_int]
         L.sky_oracle_strerror.restype = ctypes.c_char_p
         _lib = L
@@ -143,3 +147,24 @@ def chunk_stage(data):
     if r < 0:
         raise OracleError(int(r))
     return out.raw[:r], dig.raw
+
+
+def secretbox_seal(key: bytes, nonce: bytes, msg) -> bytes:
+    """tag(16) || ciphertext, i.e. nacl.bindings.crypto_secretbox(msg, nonce, key) (SecretBox.encrypt minus the nonce prefix)."""
+    assert len(key) == 32 and len(nonce) == 24
+    p, n, _k = _ro(msg)
+    out = ctypes.create_string_buffer(16 + n)
+    lib().sky_oracle_secretbox_seal(ctypes.cast(ctypes.c_char_p(key), ctypes.c_void_p), ctypes.cast(ctypes.c_char_p(nonce), ctypes.c_void_p),
+                                    p, n, ctypes.cast(out, ctypes.c_void_p))
+    return out.raw
+
+
+def secretbox_open(key: bytes, nonce: bytes, boxed) -> bytes:
+    assert len(key) == 32 and len(nonce) == 24
+    p, n, _k = _ro(boxed)
+    out = ctypes.create_string_buffer(max(1, n))
+    rc = lib().sky_oracle_secretbox_open(ctypes.cast(ctypes.c_char_p(key), ctypes.c_void_p), ctypes.cast(ctypes.c_char_p(nonce), ctypes.c_void_p),
+                                         p, n, ctypes.cast(out, ctypes.c_void_p))
+    if rc != 0:
+        raise ValueError("secretbox: authentication failed")
+    return out.raw[: n - 16]

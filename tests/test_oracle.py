@@ -217,3 +217,23 @@ try:
             assert ref.lz4f_decompress(frame[: len(frame)], max(raw, 1))[: len(out)] == out
 except ImportError:  # hypothesis not installed: the parametrised differential tests above still run
     pass
+
+
+# ---------------------------------------------------------------- XSalsa20-Poly1305 groundwork
+def test_secretbox_matches_pynacl():
+    """The reference encrypts the compressed frame with nacl.secret.SecretBox (gateway_operator.py:362-364); PyNaCl is
+    installed here, so the restatement is pinned against the reference's own engine."""
+    nacl_secret = pytest.importorskip("nacl.secret")
+    rng = np.random.default_rng(8)
+    for n in [0, 1, 15, 16, 17, 31, 32, 33, 63, 64, 65, 100, 1000, 4096, 65537, 300001]:
+        key, nonce, msg = rng.bytes(32), rng.bytes(24), rng.bytes(n)
+        box = nacl_secret.SecretBox(key)
+        want = bytes(box.encrypt(msg, nonce))  # nonce || tag || ciphertext
+        got = oracle.secretbox_seal(key, nonce, msg)
+        assert nonce + got == want, n
+        assert oracle.secretbox_open(key, nonce, got) == msg == box.decrypt(want)
+        if n:
+            bad = bytearray(got)
+            bad[-1] ^= 1
+            with pytest.raises(ValueError):
+                oracle.secretbox_open(key, nonce, bytes(bad))
