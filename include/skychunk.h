@@ -50,9 +50,11 @@ extern "C" {
 /* stage selection for sky_process_device (0 = both) */
 #define SKY_F_LZ4 1u
 #define SKY_F_MD5 2u
-/* keep the SM sub-partition that hosts an MD5 warp free of LZ4 warps */
+/* keep the SM sub-partition that hosts an MD5 warp free of LZ4 warps (applied automatically when the batch has
+ * at most one MD5 group per SM, i.e. <= 32 x SM-count chunks; the flag forces it for larger batches) */
 #define SKY_F_MD5_EXCLUSIVE 4u
-/* do not pace LZ4 work to the MD5 lanes' progress (pacing lets the lanes read the input from L2) */
+/* do not pace LZ4 work to the MD5 lanes' progress (pacing lets the lanes read the input from L2; sky_submit always
+ * runs unpaced so that the kernels of different slots overlap) */
 #define SKY_F_NO_PACING 8u
 
 typedef struct sky_ctx sky_ctx;
