@@ -8,10 +8,10 @@ and the daemon consumes in ``create_gateway_operators`` (skyplane/gateway/gatewa
 Wiring rules kept from the reference: a node's handle is ``<op_type>_<handle>``; an operator whose first child
 is ``mux_and`` feeds a ``GatewayANDQueue`` (every grandchild sees every chunk), ``mux_or`` children share the
 private queue their ``mux_and`` parent gave them, operators without children are terminal, an unknown ``op_type``
-raises ``ValueError``.  Only the op types of the B200 stage are built in (``compress_hash`` between
-``read_object_store`` and ``send`` on the source gateway, ``decompress_verify`` before ``write_object_store`` on the
-destination gateway); the daemon's own operators (object store, sender, receiver) are supplied by the caller
-through ``factories`` so this module stays free of cloud / socket code.
+raises ``ValueError``.  Built in: the B200 stage's op types (``compress_hash`` between ``read_object_store`` and
+``send`` on the source gateway, ``decompress_verify`` before ``write_object_store`` on the destination gateway) and the
+reference's three file-only operators (``receive``, ``gen_data``, ``write_local``); the daemon's cloud / socket
+operators (object store, sender) are supplied by the caller through ``factories``.
 """
 from __future__ import annotations
 
@@ -41,7 +41,27 @@ def _decompress_verify(op: Dict, kw: Dict) -> GatewayOperator:
     return GatewayDecompressVerify(**kw, n_processes=op.get("num_gpus", 1), n_gpus=op.get("num_gpus"))
 
 
-BUILTIN_FACTORIES: Dict[str, Factory] = {"compress_hash": _compress_hash, "decompress_verify": _decompress_verify}
+def _receive(op: Dict, kw: Dict) -> GatewayOperator:
+    from skyplane_b200.local_operators import GatewayWaitReceiver
+
+    return GatewayWaitReceiver(**kw, n_processes=1)
+
+
+def _gen_data(op: Dict, kw: Dict) -> GatewayOperator:
+    from skyplane_b200.local_operators import GatewayRandomDataGen
+
+    return GatewayRandomDataGen(**kw, size_mb=op["size_mb"], fill=op.get("fill", "zeros"))
+
+
+def _write_local(op: Dict, kw: Dict) -> GatewayOperator:
+    from skyplane_b200.local_operators import GatewayWriteLocal
+
+    return GatewayWriteLocal(**kw, n_processes=1)
+
+
+# op types that need neither cloud SDKs nor sockets; read/write_object_store and send come from the caller
+BUILTIN_FACTORIES: Dict[str, Factory] = {"compress_hash": _compress_hash, "decompress_verify": _decompress_verify,
+                                         "receive": _receive, "gen_data": _gen_data, "write_local": _write_local}
 _MUX = ("mux_and", "mux_or")
 
 

@@ -560,3 +560,52 @@ def test_harness_stream_with_stub_operator(tmp_path):
         assert r["md5"] == hashlib.md5(datas[r["pool_index"]]).hexdigest()
         assert Path(r["frame_path"]).exists() and not (tmp_path / "chunks" / f"{r['chunk_id']}.chunk").exists()
     assert res["wall_s"] > 0
+
+
+def test_local_operators_pipeline_from_program_json(tmp_path):
+    """gen_data -> compress_hash -> write_local wired from a reference-schema program; wait-receive semantics."""
+    import hashlib
+
+    import oracle
+    from skyplane_b200.local_operators import GatewayRandomDataGen, GatewayWaitReceiver
+    from skyplane_b200.program import build_operator_graph
+
+    cs = ChunkStore(tmp_path)
+    ev, eq = mp.Event(), mp.Queue()
+    # wait-receive: missing -> False, short -> False, complete -> True (gateway_operator.py:131-150)
+    wr = GatewayWaitReceiver("receive_x", "r", GatewayQueue(), None, ev, eq, cs)
+    req = ChunkRequest(Chunk("k", "k", "aa" * 16, 10))
+    assert wr.process(req) is False
+    cs.get_chunk_file_path("aa" * 16).write_bytes(b"12345")
+    assert wr.process(req) is False
+    cs.get_chunk_file_path("aa" * 16).write_bytes(b"1234567890")
+    assert wr.process(req) is True
+    with pytest.raises(ValueError):
+        GatewayRandomDataGen("g", "r", GatewayQueue(), None, ev, eq, cs, size_mb=1, fill="ones")
+
+    program = [{"partitions": ["0"], "value": [{"op_type": "gen_data", "handle": "g", "size_mb": 0.25, "fill": "random", "children": [
+        {"op_type": "compress_hash", "handle": "c", "num_gpus": 1, "children": [{"op_type": "write_local", "handle": "w", "children": []}]}]}]}]
+    g = build_operator_graph(program, cs, "r", ev, eq,
+                             {"compress_hash": lambda op, kw: _StubbedCompressHash(**kw, n_processes=1, max_batch_chunks=4, read_threads=1)})
+    assert list(g.operators) == ["gen_data_g", "compress_hash_c", "write_local_w"] and g.terminal_operators == {"0": ["write_local_w"]}
+    g.start()
+    try:
+        ids = ["%032x" % (0xB200 + i) for i in range(5)]
+        for cid in ids:
+            cs.add_chunk_request(ChunkRequest(Chunk("gen", "gen", cid, 0, partition_id="0"), src_type="random", src_random_size_mb=1))
+        done = set()
+        t0 = time.time()
+        while len(done) < len(ids) and time.time() - t0 < 30 and not ev.is_set():
+            try:
+                rec = cs.chunk_status_queue.get(timeout=0.2)
+            except queue.Empty:
+                continue
+            if rec["handle"] == "write_local_w" and rec["state"] == "complete":
+                done.add(rec["chunk_id"])
+        assert done == set(ids) and not ev.is_set()
+        for cid in ids:
+            data = cs.get_chunk_file_path(cid).read_bytes()
+            assert len(data) == 262144
+            assert oracle.lz4f_decode(cs.get_compressed_file_path(cid).read_bytes(), len(data)) == data
+    finally:
+        g.stop()
