@@ -129,8 +129,16 @@ __device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__r
 }
 
 // Ask L2 to fetch [p, p+bytes) (bytes multiple of 16, p 16-byte aligned); one thread issues it.
+// -DSKY_L2_EVICT_LAST=1 tags the row evict-last so it survives until the MD5 lanes have read it (experiment for the
+// 1.21x DRAM traffic of config 2; off by default, not yet measured).
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
+#if SKY_L2_EVICT_LAST
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
+#else
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
 }
 
 // ---- XXH32 of the frame descriptor (2 or 10 bytes), for the header checksum byte -----------------
@@ -233,6 +241,12 @@ __device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src,
     }
 }
 
+#ifndef SKY_BACK_EXT_ALWAYS
+#define SKY_BACK_EXT_ALWAYS 0
+#endif
+#ifndef SKY_L2_EVICT_LAST
+#define SKY_L2_EVICT_LAST 0
+#endif
 #ifndef SKY_EXT_ROUNDS
 #define SKY_EXT_ROUNDS 7
 #endif
@@ -348,8 +362,10 @@ __device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict
             const uint32_t e_mine = pos + mlen;
             uint32_t prev_end = __shfl_sync(kFull, e_mine, prev_l < 0 ? 0 : prev_l);
             if (prev_l < 0) prev_end = anchor;
-            // ---- backward extension ("catch up"); only probes that skipped positions can gain from it
-            if (step > 1 && is_sel) {
+            // ---- backward extension ("catch up").  Default: only probes that skipped positions (step > 1).
+            // -DSKY_BACK_EXT_ALWAYS=1 extends every accepted match: +1.5 % ratio on the Silesia-like set in the CPU
+            // model (tools/ratio_study.py) for one more dependent load per window -- to be measured on the GPU.
+            if ((SKY_BACK_EXT_ALWAYS || step > 1) && is_sel) {
                 const uint32_t room = min(pos - prev_end, cand);
                 uint32_t b = 0;
                 while (b < room && src[pos - 1 - b] == src[cand - 1 - b]) b++;
