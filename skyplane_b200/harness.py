@@ -130,7 +130,14 @@ def run_stream(
             _drain_status(store, status_acc)
             time.sleep(0.002)
         op.stop_workers()
-    _drain_status(store, status_acc)
+    # this process logged the "registered" records itself: give its feeder thread a moment to flush them, drain, and do
+    # not let interpreter exit block on records nobody will read
+    for _ in range(50):
+        _drain_status(store, status_acc)
+        if sum(status_acc["states"].values()) >= 3 * sent:
+            break
+        time.sleep(0.01)
+    store.chunk_status_queue.cancel_join_thread()
     status, comp, raw = status_acc["states"], status_acc["comp"], status_acc["raw"]
     return {"wall_s": wall, "bytes": total_bytes, "records": records, "status": status, "compressed_bytes": comp, "uncompressed_bytes": raw}
 
