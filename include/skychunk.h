@@ -63,6 +63,13 @@ SKY_API const char *sky_strerror(int code);
 SKY_API const char *sky_last_error(const sky_ctx *ctx); /* detail of the last SKY_E_CUDA on this ctx */
 SKY_API int sky_abi_version(void);
 SKY_API int sky_device_count(int *count);
+/* PCI bus id ("0000:1b:00.0") of CUDA device `device` as the CUDA runtime orders devices (honours CUDA_VISIBLE_DEVICES,
+ * unlike nvidia-smi -i); the host side maps it to the GPU's NUMA node before pinning staging memory. */
+SKY_API int sky_device_pci_bus_id(int device, char *buf, int len);
+/* Compile-time constants of the kernels in this build (tuning builds differ): what = 0 -> LZ4 match-table entries per
+ * warp, 1 -> warps per CTA of the fused kernel, 2 -> probe slots per tile, 3 -> log2 of the largest probe stride.
+ * Unknown `what` returns 0.  Parity tests feed these to the sequential twin of the compressor (tools/lz4_tile_model.c). */
+SKY_API uint32_t sky_kernel_config(int what);
 
 /* Worst-case frame bytes for an n-byte chunk: 15 + n + 4*ceil(n/65536) + 4 (11 when n == 0). */
 SKY_API uint64_t sky_frame_bound(uint64_t n);

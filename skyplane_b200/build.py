@@ -11,7 +11,11 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libskychunk.so"
 SOURCES = [CSRC / "skychunk.cu"]
-DEPS = [CSRC / "skychunk.cu", CSRC / "lz4.cuh", CSRC / "md5.cuh", PKG.parent / "include" / "skychunk.h"]
+
+
+def _deps():
+    return sorted(CSRC.glob("*.cu*")) + sorted((PKG.parent / "include").glob("*.h"))
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -32,7 +36,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     t = LIB.stat().st_mtime
-    return any(d.stat().st_mtime > t for d in DEPS)
+    return any(d.stat().st_mtime > t for d in _deps())
 
 
 def build_variant(out: Path, defines: dict, verbose: bool = False) -> Path:
@@ -50,10 +54,14 @@ def build_variant(out: Path, defines: dict, verbose: bool = False) -> Path:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, SOURCES)]
+    # build next to the target and rename into place: concurrent builders (forked workers) never load a partial file
+    tmp = LIB.with_name(f".{LIB.name}.{os.getpid()}.tmp")
+    cmd = [nvcc_path(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(tmp), *map(str, SOURCES)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"nvcc failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     if verbose:
         print(r.stderr, file=sys.stderr)
     return LIB

@@ -17,15 +17,14 @@ namespace sky {
 
 constexpr uint32_t kBlock = 65536;       // BD = 0x40
 constexpr uint32_t kSlot = kBlock + 4;   // worst-case block footprint in the frame (header + raw data)
-#ifndef SKY_HASHLOG
-#define SKY_HASHLOG 12
+#ifndef SKY_LZ4_ENTRIES
+#define SKY_LZ4_ENTRIES 4096
 #endif
-constexpr uint32_t kHashLog = SKY_HASHLOG;
-constexpr uint32_t kHashSize = 1u << kHashLog;
+constexpr uint32_t kEntries = SKY_LZ4_ENTRIES;  // match-table entries per warp (u32 each: pos16 | tag16); any multiple of 128
+constexpr uint32_t kTableBytes = kEntries * 4;
 constexpr uint32_t kMinMatch = 4;
 constexpr uint32_t kMfLimit = 12;        // a match must start >= 12 bytes before the block end
 constexpr uint32_t kLastLiterals = 5;    // the last 5 bytes are always literals
-constexpr uint32_t kSkipTrigger = 6;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---- unaligned little-endian 32-bit read from global memory (base 4-byte aligned) --------------
@@ -34,8 +33,6 @@ __device__ __forceinline__ uint32_t load32(const uint8_t *base, uint32_t pos) {
     const uint32_t lo = __ldg(w), hi = __ldg(w + 1);
     return __funnelshift_r(lo, hi, (pos & 3u) * 8u);
 }
-
-__device__ __forceinline__ uint32_t lz4_hash(uint32_t v) { return (v * 2654435761u) >> (32 - kHashLog); }
 
 // ---- warp copy: dst and src arbitrarily aligned; regions disjoint, or dst < src (forward move) ----
 // Over-reads at most 3 bytes past src+n (inside the same 4-byte word group); never over-writes.
@@ -84,9 +81,16 @@ __device__ __forceinline__ void warp_copy(uint8_t *dst, const uint8_t *src, uint
     if (lane < tail) dst[done + lane] = tb;
 }
 
-// ---- warp copy for DISJOINT regions whose source is kernel-read-only input (ld.global.nc), 4 x 16 B in
-// flight per lane.  src 16-byte aligned; dst arbitrary.
-__device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t n, unsigned lane) {
+// ---- streaming warp copy for DISJOINT regions: 16-byte loads (4 in flight per lane), 16-byte streaming stores (the
+// frame is never re-read here: keep L2 for the input rows and the scratch).  src 16-byte aligned; dst arbitrary.
+// kReadOnly: the source is kernel-read-only input (ld.global.nc); otherwise it was written by this warp (ld.global.cg).
+template <bool kReadOnly>
+__device__ __forceinline__ uint32_t ld_stream32(const uint32_t *p) { return kReadOnly ? __ldg(p) : __ldcg(p); }
+template <bool kReadOnly>
+__device__ __forceinline__ uint4 ld_stream128(const uint4 *p) { return kReadOnly ? __ldg(p) : __ldcg(p); }
+
+template <bool kReadOnly>
+__device__ __forceinline__ void warp_copy_stream(uint8_t *dst, const uint8_t *__restrict__ src, uint32_t n, unsigned lane) {
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
     if (mis == 0) {
         const uint4 *sv = reinterpret_cast<const uint4 *>(src);
@@ -94,10 +98,11 @@ __device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__r
         const uint32_t nvec = n >> 4;
         uint32_t k = lane;
         for (; k + 96 < nvec; k += 128) {
-            const uint4 a = __ldg(sv + k), b = __ldg(sv + k + 32), c = __ldg(sv + k + 64), d = __ldg(sv + k + 96);
+            const uint4 a = ld_stream128<kReadOnly>(sv + k), b = ld_stream128<kReadOnly>(sv + k + 32),
+                        c = ld_stream128<kReadOnly>(sv + k + 64), d = ld_stream128<kReadOnly>(sv + k + 96);
             __stcs(dv + k, a); __stcs(dv + k + 32, b); __stcs(dv + k + 64, c); __stcs(dv + k + 96, d);
         }
-        for (; k < nvec; k += 32) __stcs(dv + k, __ldg(sv + k));
+        for (; k < nvec; k += 32) __stcs(dv + k, ld_stream128<kReadOnly>(sv + k));
         const uint32_t done = nvec << 4;
         if (lane < (n & 15u)) dst[done + lane] = src[done + lane];
         return;
@@ -115,14 +120,15 @@ __device__ __forceinline__ void warp_copy_input(uint8_t *dst, const uint8_t *__r
     const uint32_t wsh = head >> 2, bsh = (head & 3u) * 8u;
     for (uint32_t k = lane; k < nvec; k += 32) {
         const uint32_t *q = sw + wsh + 4 * (size_t)k;
-        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3);
-        const uint32_t w4 = bsh ? __ldg(q + 4) : 0u;
+        const uint32_t w0 = ld_stream32<kReadOnly>(q), w1 = ld_stream32<kReadOnly>(q + 1), w2 = ld_stream32<kReadOnly>(q + 2),
+                       w3 = ld_stream32<kReadOnly>(q + 3);
+        const uint32_t w4 = bsh ? ld_stream32<kReadOnly>(q + 4) : 0u;
         uint4 o;
         o.x = __funnelshift_r(w0, w1, bsh);
         o.y = __funnelshift_r(w1, w2, bsh);
         o.z = __funnelshift_r(w2, w3, bsh);
         o.w = __funnelshift_r(w3, w4, bsh);
-        __stcs(dv + k, o);  // streaming: the frame is never re-read here, keep L2 for the input rows
+        __stcs(dv + k, o);
     }
     const uint32_t done = head + (nvec << 4);
     if (lane < (rem & 15u)) dst[done + lane] = src[done + lane];
@@ -241,193 +247,210 @@ __device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src,
     }
 }
 
-#ifndef SKY_BACK_EXT_ALWAYS
-#define SKY_BACK_EXT_ALWAYS 0
-#endif
-#ifndef SKY_L2_EVICT_LAST
-#define SKY_L2_EVICT_LAST 0
-#endif
-#ifndef SKY_EXT_ROUNDS
-#define SKY_EXT_ROUNDS 7
-#endif
 #ifndef SKY_COOP_LIT
-#define SKY_COOP_LIT 48
+#define SKY_COOP_LIT 16
 #endif
-constexpr int kExtRounds = SKY_EXT_ROUNDS;     // per-lane extension: up to 4 + 4*rounds bytes before going cooperative
-constexpr uint32_t kCoopLit = SKY_COOP_LIT;    // literal runs at least this long are copied by the whole warp
+#ifndef SKY_MAX_STEP_LOG
+#define SKY_MAX_STEP_LOG 4
+#endif
+constexpr uint32_t kCoopLit = SKY_COOP_LIT;          // literal runs at least this long are copied by the whole warp
+constexpr uint32_t kMaxStepLog = SKY_MAX_STEP_LOG;   // probe stride doubles after a tile without a hit, up to 1 << this
+constexpr int kGroups = 8;                           // a tile = 8 warp-wide groups = 256 probe slots
+constexpr uint32_t kTile = kGroups * 32;
+constexpr uint32_t kOffsBytes = kTile * 2;           // per-warp u16 offsets of the current tile's slots
+constexpr uint32_t kLz4AreaBytes = kTableBytes + kOffsBytes;
+constexpr uint32_t kScratchBytes = kBlock + 1024;    // per-warp compressed-block scratch (output can overshoot L by < 300 B)
 
-// ---- the block compressor -------------------------------------------------------------------------
-// src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: where compressed
-// bytes may be written (capacity L bytes), ht: this warp's match table.
-// Returns the compressed size (1..L-1), or 0 if the block does not shrink (caller stores it raw).
-//
-// One iteration handles a whole window of 32 cursor positions: every lane probes its position, lanes with a
-// verified candidate extend their own match (lane-parallel), then matches are accepted greedily in position
-// order (a match is skipped if it starts inside an accepted one -- exactly what the sequential reference
-// does), and all accepted sequences are sized with a warp scan and written by their own lanes at once.
-__device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict__ src, uint32_t L, uint8_t *__restrict__ out,
-                                                      uint16_t *ht, unsigned lane) {
-    {   // clear the table: 32 lanes x 16 B per round
-        uint4 *t4 = reinterpret_cast<uint4 *>(ht);
-        const uint4 z = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return (x * 0x8081u) >> 23; }  // exact for x < 65536
+
+// ---- emission of up to 32 recorded sequences, one per lane ------------------------------------------
+// q0 = literal length | match length << 16, q1 = literal start | offset << 16 (lane k = k-th sequence).
+// Sizes go through a warp scan; every lane writes its own token, length bytes, literals (runs >= kCoopLit: one warp
+// copy each), offset and match-length bytes.  Returns the new output cursor.  Not inlined: called from two places.
+__device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t op, const uint8_t *__restrict__ src, uint32_t q0,
+                                            uint32_t q1, uint32_t nseq, unsigned lane) {
+    const bool act = lane < nseq;
+    const uint32_t ll = q0 & 0xffffu, ml = q0 >> 16, lit = q1 & 0xffffu, off = q1 >> 16;
+    const uint32_t mcode = ml - kMinMatch;
+    const uint32_t nl = ll >= 15 ? div255(ll - 15) + 1 : 0, nm = mcode >= 15 ? div255(mcode - 15) + 1 : 0;
+    const uint32_t sz = act ? 3 + ll + nl + nm : 0;
+    uint32_t incl = sz;
 #pragma unroll
-        for (int k = 0; k < (int)(kHashSize * 2 / 16 / 32); k++) t4[k * 32 + lane] = z;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, d);
+        if ((int)lane >= d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    uint32_t lit_o = 0;
+    if (act) {
+        uint32_t o = op + incl - sz;
+        out[o++] = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mcode < 15 ? mcode : 15));
+        if (nl) {
+            for (uint32_t k = 0; k + 1 < nl; k++) out[o + k] = 255;
+            out[o + nl - 1] = (uint8_t)(ll - 15 - (nl - 1) * 255);
+            o += nl;
+        }
+        lit_o = o;
+        if (ll < kCoopLit) {
+            uint32_t k = 0;
+            for (; k + 4 <= ll; k += 4) {  // 4 literal bytes per round: one unaligned read, four byte stores
+                const uint32_t w = load32(src, lit + k);
+                out[o + k] = (uint8_t)w;
+                out[o + k + 1] = (uint8_t)(w >> 8);
+                out[o + k + 2] = (uint8_t)(w >> 16);
+                out[o + k + 3] = (uint8_t)(w >> 24);
+            }
+            const uint32_t rem = ll - k;
+            if (rem) {  // (literals of a match sequence end >= 12 bytes before the block end: the word read is in range)
+                const uint32_t w = load32(src, lit + k);
+                out[o + k] = (uint8_t)w;
+                if (rem > 1) out[o + k + 1] = (uint8_t)(w >> 8);
+                if (rem > 2) out[o + k + 2] = (uint8_t)(w >> 16);
+            }
+        }
+        o += ll;
+        out[o] = (uint8_t)off;
+        out[o + 1] = (uint8_t)(off >> 8);
+        o += 2;
+        if (nm) {
+            for (uint32_t k = 0; k + 1 < nm; k++) out[o + k] = 255;
+            out[o + nm - 1] = (uint8_t)(mcode - 15 - (nm - 1) * 255);
+        }
     }
     __syncwarp();
+    unsigned big = __ballot_sync(kFull, act && ll >= kCoopLit);
+    while (big) {  // long literal runs: one warp-wide copy each
+        const int l = __ffs(big) - 1;
+        big &= big - 1;
+        warp_copy(out + __shfl_sync(kFull, lit_o, l), src + __shfl_sync(kFull, lit, l), __shfl_sync(kFull, ll, l), lane);
+    }
+    return op + total;
+}
 
-    uint32_t ip = 0, anchor = 0, op = 0;
+// ---- the block compressor -------------------------------------------------------------------------
+// src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: this warp's scratch (kScratchBytes),
+// tab: this warp's shared-memory area (kLz4AreaBytes: match table, then the tile's slot offsets).
+// Returns the compressed size (1..L-1), or 0 if the block does not shrink (caller stores it raw).
+//
+// The block is parsed tile by tile (kTile probe slots at stride 1 << slog), three decoupled phases per tile, each with
+// all 32 lanes busy (tools/lz4_tile_model.c is the sequential twin of exactly these rules):
+//   pass 1  every slot: read 5 bytes, hash, ONE shared-memory lookup of (pos16 | tag16); a hit is a tag match, no byte of
+//           the candidate is read.  Lanes of a group that hash alike are ordered with one match.any so the result equals
+//           sequential insertion (nearest lower lane = most recent occurrence; the highest lane stores).
+//   pass 2  greedy parse over the hit bit masks: per accepted match one warp-wide round compares 24 bytes ahead and 8
+//           bytes behind (coalesced byte loads) -- verification, forward and backward extension in one ballot; longer
+//           matches continue 128 bytes per round.  Sequences are recorded one per lane.
+//   pass 3  every 32 sequences: flush_seqs (scan of sizes, lane-parallel emission).
+__device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict__ src, uint32_t L, uint8_t *__restrict__ out,
+                                                      uint32_t *tab, unsigned lane) {
+    {   // clear the table: 32 lanes x 16 B per round; entry 0 = (position 0, tag 0) doubles as "empty"
+        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+        for (uint32_t k = lane; k < kEntries / 4; k += 32) t4[k] = z;
+    }
+    uint16_t *offs = reinterpret_cast<uint16_t *>(tab + kEntries);
+    __syncwarp();
+
+    uint32_t anchor = 0, cur = 0, op = 0, nseq = 0, q0 = 0, q1 = 0;
     const uint32_t limit = L - 1;  // accept only csize <= L-1 (LZ4F_makeBlock passes dstCapacity = srcSize-1)
     const unsigned lt_mask = (1u << lane) - 1u;
 
     if (L >= kMfLimit + 1) {
         const uint32_t mflimit = L - kMfLimit;          // last position a match may start at
         const uint32_t matchlimit = L - kLastLiterals;  // matches end at or before this
-        uint32_t nprobe = 1u << kSkipTrigger;           // LZ4: searchMatchNb = acceleration << skipTrigger
-        while (ip <= mflimit) {
-            const uint32_t step = nprobe >> kSkipTrigger;
-            uint32_t pos = ip + lane * step;
-            const bool valid = pos <= mflimit;
-            uint32_t v = 0, h = 0, cand = 0;
-            if (valid) {
-                v = load32(src, pos);
-                h = lz4_hash(v);
-                cand = ht[h];
+        const uint32_t *W = reinterpret_cast<const uint32_t *>(src);
+        const int dl = lane < 24 ? (int)lane : 23 - (int)lane;  // byte this lane compares: +0..+23 ahead, -1..-8 behind
+        uint32_t tb = 0, slog = 0;
+        while (tb <= mflimit) {
+            const uint32_t span = kTile << slog;
+            if (lane == 0) {  // pull the tile after next towards L2 (the MD5 lanes of the chunk share it)
+                const uint32_t pf = (tb + 2 * span) & ~15u;
+                if (pf < L) l2_prefetch_bulk(src + pf, min(span, ((L - pf) + 15u) & ~15u));
             }
-            bool hit = valid && cand < pos && load32(src, cand) == v;
-            // Lanes that hash to the same slot are grouped with one match.any: (a) the nearest lower lane of the
-            // group is the most recent occurrence inside the window (offsets below 32*step: runs, short periods,
-            // repeated words), which the table cannot know yet -- like the sequential reference, the most recent
-            // occurrence wins; (b) only the highest lane of a group stores its position, so the table update is
-            // deterministic and free of same-instruction write-write conflicts.
-            const unsigned vmask = __ballot_sync(kFull, valid);
-            const unsigned grp = __match_any_sync(kFull, valid ? h : (0xffff0000u | lane)) & vmask;
-            {
-                const unsigned lower = grp & lt_mask;
-                const int near = lower ? 31 - __clz(lower) : 0;
-                const uint32_t v_near = __shfl_sync(kFull, v, near);
-                if (valid && lower && v_near == v) {
-                    cand = ip + (uint32_t)near * step;
-                    hit = true;
-                }
-            }
-            const unsigned hits = __ballot_sync(kFull, hit);  // (also orders the table reads before the writes)
-            // every probed position enters the table: the cursor always moves past the whole window, so no
-            // entry can point ahead of a later probe
-            if (valid && (grp >> lane) == 1u) ht[h] = (uint16_t)pos;
-            __syncwarp();
-            if (hits == 0) {
-                ip += 32 * step;
-                nprobe += 32;
-                continue;
-            }
-            // ---- lane-parallel forward extension (bounded); `more` = still matching at the bound
-            uint32_t mlen = 0;
-            bool more = false;
-            if (hit) {
-                const uint32_t maxlen = matchlimit - pos;  // >= 7
-                mlen = kMinMatch;
-                more = true;
-#pragma unroll 1
-                for (int r = 0; r < kExtRounds && mlen < maxlen; r++) {
-                    const uint32_t x = load32(src, pos + mlen) ^ load32(src, cand + mlen);
-                    if (x) {
-                        mlen += (uint32_t)(__ffs(x) - 1) >> 3;
-                        more = false;
-                        break;
-                    }
-                    mlen += 4;
-                }
-                if (mlen >= maxlen) {
-                    mlen = maxlen;
-                    more = false;
-                }
-            }
-            __syncwarp();
-            // ---- greedy acceptance in position order
-            unsigned sel = 0, rem = hits;
-            while (rem) {
-                const int l = __ffs(rem) - 1;
-                const uint32_t p_l = ip + (uint32_t)l * step;
-                uint32_t len_l = __shfl_sync(kFull, mlen, l);
-                if (__shfl_sync(kFull, (int)more, l)) {  // long match: finish it with the whole warp
-                    len_l = extend_coop(src, p_l, __shfl_sync(kFull, cand, l), len_l, matchlimit - p_l, lane);
-                    if ((int)lane == l) mlen = len_l;
-                }
-                sel |= 1u << l;
-                rem &= __ballot_sync(kFull, pos >= p_l + len_l);  // drop every hit that starts inside this match
-            }
-            const bool is_sel = (sel >> lane) & 1u;
-            const unsigned before = sel & lt_mask;
-            const int prev_l = before ? 31 - __clz(before) : -1;
-            const uint32_t e_mine = pos + mlen;
-            uint32_t prev_end = __shfl_sync(kFull, e_mine, prev_l < 0 ? 0 : prev_l);
-            if (prev_l < 0) prev_end = anchor;
-            // ---- backward extension ("catch up").  Default: only probes that skipped positions (step > 1).
-            // -DSKY_BACK_EXT_ALWAYS=1 extends every accepted match: +1.5 % ratio on the Silesia-like set in the CPU
-            // model (tools/ratio_study.py) for one more dependent load per window -- to be measured on the GPU.
-            if ((SKY_BACK_EXT_ALWAYS || step > 1) && is_sel) {
-                const uint32_t room = min(pos - prev_end, cand);
-                uint32_t b = 0;
-                while (b < room && src[pos - 1 - b] == src[cand - 1 - b]) b++;
-                pos -= b;
-                cand -= b;
-                mlen += b;
-            }
-            const uint32_t ll = is_sel ? pos - prev_end : 0;
-            const uint32_t sz = is_sel ? seq_bytes(ll, mlen) : 0;
-            uint32_t incl = sz;
+            // ---- pass 1
+            uint32_t mymask = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(kFull, incl, d);
-                if ((int)lane >= d) incl += t;
-            }
-            const uint32_t total = __shfl_sync(kFull, incl, 31);
-            if (op + total + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
-            uint32_t lit_o = 0;
-            if (is_sel) {
-                uint32_t o = op + incl - sz;
-                const uint32_t mcode = mlen - kMinMatch;
-                out[o++] = (uint8_t)(((ll < 15 ? ll : 15) << 4) | (mcode < 15 ? mcode : 15));
-                if (ll >= 15) {
-                    uint32_t r = ll - 15;
-                    for (; r >= 255; r -= 255) out[o++] = 255;
-                    out[o++] = (uint8_t)r;
+            for (int g = 0; g < kGroups; g++) {
+                const uint32_t p = tb + ((uint32_t)(g * 32 + lane) << slog);
+                const bool valid = p <= mflimit;
+                uint32_t mine = 0, idx = 0xffff0000u | lane, e = 0;
+                if (valid) {
+                    const uint32_t w0 = __ldg(W + (p >> 2)), w1 = __ldg(W + (p >> 2) + 1);
+                    const uint32_t sh = (p & 3u) * 8u;
+                    uint32_t hf = __funnelshift_r(w0, w1, sh) * 2654435761u;
+                    hf = ((w1 >> sh) & 0xffu) * 0x85EBCA6Bu + hf;  // fifth byte
+                    idx = __umulhi(hf, kEntries);
+                    mine = __byte_perm(p, hf, 0x6510);  // pos16 | hash bytes 1-2 as the tag
+                    e = tab[idx];
                 }
-                lit_o = o;
-                if (ll < kCoopLit) {
-                    uint32_t k = 0;
-                    for (; k + 4 <= ll; k += 4) {  // 4 literal bytes per round: one unaligned read, four byte stores
-                        const uint32_t w = load32(src, prev_end + k);
-                        out[o + k] = (uint8_t)w;
-                        out[o + k + 1] = (uint8_t)(w >> 8);
-                        out[o + k + 2] = (uint8_t)(w >> 16);
-                        out[o + k + 3] = (uint8_t)(w >> 24);
-                    }
-                    for (; k < ll; k++) out[o + k] = src[prev_end + k];
+                const unsigned grp = __match_any_sync(kFull, idx);
+                const unsigned lower = grp & lt_mask;
+                const uint32_t e_near = __shfl_sync(kFull, mine, lower ? 31 - __clz(lower) : 0);
+                if (lower) e = e_near;  // a lower lane of this group filled the slot more recently than the table knows
+                const uint32_t x = e ^ mine;
+                const unsigned hits = __ballot_sync(kFull, valid && x < 65536u && x != 0u);  // (also: table reads before writes)
+                if ((int)lane == g) mymask = hits;
+                offs[g * 32 + lane] = (uint16_t)(mine - e);
+                if (valid && (grp >> lane) == 1u) tab[idx] = mine;
+                __syncwarp();
+            }
+            // ---- pass 2
+            unsigned nz = __ballot_sync(kFull, mymask != 0u);
+            const bool anyhit = nz != 0u;
+            bool accepted = false;
+            uint32_t m = 0, gbase = 0;
+            for (;;) {
+                if (m == 0) {
+                    if (nz == 0) break;
+                    const int g = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    m = __shfl_sync(kFull, mymask, g);
+                    gbase = tb + ((uint32_t)(g * 32) << slog);
                 }
-                o += ll;
-                const uint32_t offset = pos - cand;
-                out[o] = (uint8_t)offset;
-                out[o + 1] = (uint8_t)(offset >> 8);
-                o += 2;
-                if (mcode >= 15) {
-                    uint32_t r = mcode - 15;
-                    for (; r >= 255; r -= 255) out[o++] = 255;
-                    out[o++] = (uint8_t)r;
+                if (cur > gbase) {  // drop the slots the cursor has passed
+                    m &= __funnelshift_lc(0u, 0xffffffffu, (cur - gbase + (1u << slog) - 1u) >> slog);
+                    if (m == 0) continue;
+                }
+                const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+                m &= m - 1;
+                uint32_t pos = gbase + (bit << slog);
+                const uint32_t off = offs[((gbase - tb) >> slog) + bit];
+                const uint32_t cand = pos - off;
+                const uint32_t maxlen = matchlimit - pos;  // >= 7
+                const uint32_t room = min(min(pos - anchor, cand), 8u);
+                bool ok = false;
+                if (lane < 24 ? lane < maxlen : lane - 24 < room) ok = src[(int)pos + dl] == src[(int)cand + dl];
+                const unsigned eq = __ballot_sync(kFull, ok);
+                const int f = __ffs(~eq & 0xffffffu);
+                uint32_t mlen = f ? (uint32_t)(f - 1) : 24u;
+                if (mlen < kMinMatch) continue;  // tag collision (or only 4 of the 5 hashed bytes... still a valid match if >= 4)
+                if (mlen == 24u && maxlen > 24u) mlen = extend_coop(src, pos, cand, 24u, maxlen, lane);
+                const uint32_t back = (uint32_t)__ffs(~(eq >> 24)) - 1u;
+                pos -= back;
+                mlen += back;
+                const uint32_t r0 = (pos - anchor) | (mlen << 16), r1 = anchor | (off << 16);
+                if (lane == nseq) {
+                    q0 = r0;
+                    q1 = r1;
+                }
+                nseq++;
+                anchor = cur = pos + mlen;
+                accepted = true;
+                if (nseq == 32) {
+                    op = flush_seqs(out, op, src, q0, q1, 32, lane);
+                    nseq = 0;
+                    if (op + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
                 }
             }
-            __syncwarp();
-            unsigned big = __ballot_sync(kFull, is_sel && ll >= kCoopLit);
-            while (big) {  // long literal runs: one warp-wide copy each
-                const int l = __ffs(big) - 1;
-                big &= big - 1;
-                warp_copy(out + __shfl_sync(kFull, lit_o, l), src + __shfl_sync(kFull, prev_end, l), __shfl_sync(kFull, ll, l), lane);
-            }
-            op += total;
-            anchor = __shfl_sync(kFull, e_mine, 31 - __clz(sel));
-            ip = max(ip + 32 * step, anchor);
-            nprobe = 1u << kSkipTrigger;
+            tb = max(tb + span, cur);
+            if (accepted) slog = 0;
+            else if (!anyhit && slog < kMaxStepLog) slog++;
         }
+    }
+    if (nseq) {
+        op = flush_seqs(out, op, src, q0, q1, nseq, lane);
+        if (op + 1 + kLastLiterals > limit) return 0;
     }
     // last literals
     const uint32_t last = L - anchor;

@@ -44,16 +44,17 @@
 namespace sky {
 
 #ifndef SKY_WARPS
-#define SKY_WARPS 24
+#define SKY_WARPS 13
 #endif
 constexpr int kWarps = SKY_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kMd5WarpsPerCta = 4;  // warps 0..3 (one per SM sub-partition) may host MD5 groups
-constexpr uint32_t kTableBytes = kHashSize * 2;  // LZ4 match table: u16 positions
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
-constexpr uint32_t kMd5AreaBytes = kTableBytes > kRingBytes ? kTableBytes : kRingBytes;
-// warps 0..3 (MD5-capable) own kMd5AreaBytes each, the others one match table each (16 x 8 KiB = 128 KiB by default)
-constexpr uint32_t kSmemBytes = kMd5WarpsPerCta * kMd5AreaBytes + (kWarps - kMd5WarpsPerCta) * kTableBytes;
+// every warp owns one area: LZ4 match table + tile offsets, or (warps 0..3, while hosting a digest group) the MD5 ring
+constexpr uint32_t kAreaBytes = kLz4AreaBytes > kRingBytes ? kLz4AreaBytes : kRingBytes;
+constexpr uint32_t kSmemBytes = kWarps * kAreaBytes;
+static_assert(kSmemBytes <= 232448, "shared memory per CTA exceeds 227 KiB: lower SKY_WARPS or SKY_LZ4_ENTRIES");
+static_assert(kEntries % 128 == 0, "SKY_LZ4_ENTRIES must be a multiple of 128");
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
 
@@ -69,11 +70,11 @@ struct Params {
     const ChunkDesc *chunks;
     const uint32_t *md5_order;  // chunk indices, longest first, padded with 0xffffffff to 32*n_groups
     uint64_t *chain;            // per chunk OFF word: (next block index << 40) | frame offset of that block
-    uint32_t *freed;            // per chunk FREE word: leading blocks whose slots are free
     uint32_t *md5_progress;     // per MD5 group: 0 = not started, else 1 + 64 KiB rows consumed (0xffffffff = done)
     uint64_t *out_len;          // per chunk frame length
     uint8_t *md5_out;           // 16 bytes per chunk
     uint32_t *counters;         // [0] = LZ4 work counter
+    uint8_t *scratch;           // kScratchBytes per warp of the grid: where a block is compressed before its frame offset is known
     uint32_t n_chunks;
     uint32_t n_groups;
     uint32_t rows;  // max(1, max nblk)
@@ -102,8 +103,11 @@ __device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t *p) {
     return v;
 }
 
-// One LZ4 work item: block j of chunk c.
-__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint16_t *ht, unsigned lane, bool pace) {
+// One LZ4 work item: block j of chunk c.  The block is compressed into this warp's private scratch (L2-resident, reused
+// block after block); once the OFF chain says where the block starts in the frame it is written there exactly once
+// (16-byte streaming stores), or -- stored raw -- copied straight from the input.
+__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint32_t *tab, uint8_t *scratch, unsigned lane,
+                                         bool pace) {
     const ChunkDesc cd = p.chunks[c];
     if (cd.nblk == 0) {
         if (j == 0 && lane == 0) {  // empty chunk: 7-byte header + EndMark
@@ -136,14 +140,12 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
                 if (ns < 4096) ns <<= 1;
             }
         }
-        l2_prefetch_bulk(src, (L + 15u) & ~15u);
+        l2_prefetch_bulk(src, min(2048u, (L + 15u) & ~15u));  // the compressor prefetches the rest tile by tile
         if (j == 0) write_frame_header(cd.dst, cd.len);
     }
     __syncwarp();
 
-    const uint64_t slot = 15 + (uint64_t)j * kSlot;  // worst-case position of this block's header
-    uint8_t *out = cd.dst + slot + 4;
-    const uint32_t csize = lz4_compress_block(src, L, out, ht, lane);
+    const uint32_t csize = lz4_compress_block(src, L, scratch, tab, lane);
     __syncwarp();
 
     // OFF chain: learn where this block starts, tell the successor at once
@@ -157,37 +159,15 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
         }
     }
     st = __shfl_sync(kFull, st, 0);
-    const uint64_t off = st & kOffMask;  // <= slot
+    const uint64_t off = st & kOffMask;
     const uint32_t bsize = csize ? csize : L;
     const uint32_t hword = csize ? csize : (L | 0x80000000u);
     const uint64_t end = off + 4 + bsize;
     const bool last = (j + 1 == cd.nblk);
-    const bool moves = csize != 0 && off != slot;
-    if (lane == 0) {
-        if (!last) st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
-        // FREE chain: every earlier slot must be drained before this block's destination is written
-        uint32_t *fw = p.freed + c;
-        unsigned ns = 128;
-        while (ld_acquire32(fw) < j) {
-            __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
-        }
-        if (!moves) st_release32(fw, j + 1);  // this slot holds nothing a successor could clobber
-    }
-    __syncwarp();
+    if (lane == 0 && !last) st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
     uint8_t *hdr = cd.dst + off;
-    if (csize) {
-        if (moves) {
-            warp_copy(hdr + 4, out, csize, lane);  // slide left (dst < src, forward move)
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence();
-                st_release32(p.freed + c, j + 1);
-            }
-        }
-    } else {
-        warp_copy_input(hdr + 4, src, L, lane);  // stored block: straight from the input
-    }
+    if (csize) warp_copy_stream<false>(hdr + 4, scratch, csize, lane);
+    else warp_copy_stream<true>(hdr + 4, src, L, lane);  // stored block: straight from the input
     if (lane < 4) hdr[lane] = (uint8_t)(hword >> (8 * lane));
     if (last) {
         if (lane < 4) cd.dst[end + lane] = 0;  // EndMark
@@ -198,8 +178,7 @@ __device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j
 __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *my = warp < kMd5WarpsPerCta ? smem + warp * kMd5AreaBytes
-                                         : smem + kMd5WarpsPerCta * kMd5AreaBytes + (warp - kMd5WarpsPerCta) * kTableBytes;
+    uint8_t *my = smem + warp * kAreaBytes;
 
     const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
     const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
@@ -230,12 +209,13 @@ __global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) 
     }
     const bool pace = do_md5 && !(p.flags & SKY_F_NO_PACING);
     const uint32_t total = p.rows * p.n_chunks;
+    uint8_t *scratch = p.scratch + ((size_t)blockIdx.x * kWarps + warp) * kScratchBytes;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(p.counters, 1u);
         w = __shfl_sync(kFull, w, 0);
         if (w >= total) break;
-        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint16_t *>(my), lane, pace);
+        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint32_t *>(my), scratch, lane, pace);
         __syncwarp();
     }
 }
@@ -368,6 +348,7 @@ struct Slot {
     uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;  // input landed (on ctx->st_h2d) / frames landed (on ctx->st_d2h)
     uint32_t *d_counters = nullptr;
+    uint8_t *d_scratch = nullptr;  // compress scratch: kScratchBytes per warp of the grid (kernels of different slots overlap)
     // receiver side
     DecChunk *h_dchunks = nullptr, *d_dchunks = nullptr;
     DecBlock *d_dblocks = nullptr;
@@ -446,6 +427,26 @@ int sky_device_count(int *count) {
     return SKY_OK;
 }
 
+int sky_device_pci_bus_id(int device, char *buf, int len) {
+    if (!buf || len < 16) return SKY_E_INVALID;
+    cudaError_t e = cudaDeviceGetPCIBusId(buf, len, device);
+    if (e != cudaSuccess) {
+        g_err = cudaGetErrorString(e);
+        return e == cudaErrorInvalidDevice ? SKY_E_INVALID : SKY_E_NOGPU;
+    }
+    return SKY_OK;
+}
+
+uint32_t sky_kernel_config(int what) {
+    switch (what) {
+    case 0: return kEntries;
+    case 1: return (uint32_t)kWarps;
+    case 2: return kTile;
+    case 3: return kMaxStepLog;
+    default: return 0;
+    }
+}
+
 uint64_t sky_frame_bound(uint64_t n) {
     if (n == 0) return 11;
     return 15 + n + 4 * ((n + kBlock - 1) / kBlock) + 4;
@@ -468,6 +469,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
     CK(ctx, cudaMalloc(&s.d_counters, 64));
+    CK(ctx, cudaMalloc(&s.d_scratch, (size_t)ctx->sm_count * kWarps * kScratchBytes));
     CK(ctx, cudaMallocHost(&s.h_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMalloc(&s.d_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMallocHost(&s.h_dstatus, nc * sizeof(int32_t)));
@@ -489,7 +491,7 @@ static void free_slot(Slot &s) {
     cudaFreeHost(s.h_desc); cudaFreeHost(s.h_order); cudaFreeHost(s.h_chain); cudaFreeHost(s.h_outlen); cudaFreeHost(s.h_md5);
     cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters);
     cudaFreeHost(s.h_dchunks); cudaFree(s.d_dchunks); cudaFree(s.d_dblocks); cudaFree(s.d_blkdone); cudaFreeHost(s.h_dstatus); cudaFree(s.d_dstatus); cudaFree(s.d_freed); cudaFree(s.d_progress);
-    cudaFree(s.d_in); cudaFree(s.d_out);
+    cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_scratch);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_res) cudaEventDestroy(s.ev_res);
@@ -624,7 +626,6 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
         CK(ctx, cudaStreamWaitEvent(st, s.ev_h2d, 0));
     }
     CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
-    CK(ctx, cudaMemsetAsync(s.d_freed, 0, n * sizeof(uint32_t), st));
     CK(ctx, cudaMemsetAsync(s.d_progress, 0, (ng + 1) * sizeof(uint32_t), st));
     memset(s.h_outlen, 0, n * sizeof(uint64_t));  // host-side clear (mapped memory; the slot is idle here)
     memset(s.h_md5, 0, (size_t)n * 16);
@@ -633,11 +634,11 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     p.chunks = s.d_desc;
     p.md5_order = s.d_order;
     p.chain = s.d_chain;
-    p.freed = s.d_freed;
     p.md5_progress = s.d_progress;
     p.out_len = s.d_outlen;
     p.md5_out = s.d_md5;
     p.counters = s.d_counters;
+    p.scratch = s.d_scratch;
     p.n_chunks = n;
     p.n_groups = ng;
     p.rows = rows;

@@ -22,7 +22,7 @@ D_NAMES = {0: "ok", -1: "bad frame header", -2: "corrupt block", -3: "size misma
 
 # every symbol include/skychunk.h declares (tests check the .so exports exactly these)
 ABI_SYMBOLS = (
-    "sky_strerror", "sky_last_error", "sky_abi_version", "sky_device_count", "sky_frame_bound",
+    "sky_strerror", "sky_last_error", "sky_abi_version", "sky_device_count", "sky_device_pci_bus_id", "sky_kernel_config", "sky_frame_bound",
     "sky_ctx_create", "sky_ctx_destroy", "sky_pinned_alloc", "sky_pinned_free",
     "sky_submit", "sky_wait", "sky_process_device", "sky_decode_device", "sky_decode",
     "sky_device_alloc", "sky_device_free", "sky_memcpy_h2d", "sky_memcpy_d2h", "sky_launch_count",
@@ -74,6 +74,10 @@ def lib() -> ctypes.CDLL:
     L.sky_abi_version.restype = i32
     L.sky_device_count.argtypes = [ctypes.POINTER(i32)]
     L.sky_device_count.restype = i32
+    L.sky_device_pci_bus_id.argtypes = [i32, ctypes.c_char_p, i32]
+    L.sky_device_pci_bus_id.restype = i32
+    L.sky_kernel_config.argtypes = [i32]
+    L.sky_kernel_config.restype = u32
     L.sky_frame_bound.argtypes = [u64]
     L.sky_frame_bound.restype = u64
     L.sky_ctx_create.argtypes = [i32, u64, u32, u32, ctypes.POINTER(vp)]
@@ -107,6 +111,22 @@ def lib() -> ctypes.CDLL:
     L.sky_launch_count.restype = u64
     _lib = L
     return L
+
+
+def device_pci_bus_id(device: int) -> str:
+    """PCI bus id of CUDA device `device` in CUDA's own device order (honours CUDA_VISIBLE_DEVICES)."""
+    buf = ctypes.create_string_buffer(32)
+    rc = lib().sky_device_pci_bus_id(device, buf, 32)
+    if rc != SKY_OK:
+        raise SkyChunkError(rc)
+    return buf.value.decode().lower()
+
+
+def kernel_config() -> dict:
+    """Compile-time constants of the loaded build (sky_kernel_config)."""
+    L = lib()
+    return {"lz4_entries": L.sky_kernel_config(0), "warps": L.sky_kernel_config(1), "tile": L.sky_kernel_config(2),
+            "max_step_log": L.sky_kernel_config(3)}
 
 
 def frame_bound(n: int) -> int:

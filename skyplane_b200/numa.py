@@ -2,11 +2,10 @@
 
 With 8 GPUs spread over two sockets, pinned staging buffers that land on the wrong socket make every H2D/D2H
 copy cross the inter-socket link.  Called by each worker before it allocates pinned memory, so first-touch
-placement follows the affinity.  Best effort: silently does nothing when sysfs / nvidia-smi are unavailable."""
+placement follows the affinity.  Best effort: silently does nothing when sysfs or the CUDA library are unavailable."""
 from __future__ import annotations
 
 import os
-import subprocess
 from typing import List, Optional
 
 
@@ -24,12 +23,13 @@ def _parse_cpulist(text: str) -> List[int]:
 
 
 def gpu_numa_node(device: int) -> Optional[int]:
+    """NUMA node of CUDA device `device`.  The bus id comes from the CUDA runtime (sky_device_pci_bus_id), i.e. CUDA's
+    device order under CUDA_VISIBLE_DEVICES -- nvidia-smi -i indexes by PCI bus order and ignores that variable."""
     try:
-        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
-                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()[0].strip()
-        dom, bus, rest = out.split(":")
-        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{bus.lower()}:{rest.lower()}/numa_node"
-        node = int(open(path).read().strip())
+        from skyplane_b200 import native
+
+        dom, bus, rest = native.device_pci_bus_id(device).split(":")
+        node = int(open(f"/sys/bus/pci/devices/{dom[-4:]}:{bus}:{rest}/numa_node").read().strip())
         return node if node >= 0 else None
     except Exception:
         return None

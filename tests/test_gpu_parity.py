@@ -3,7 +3,8 @@ the reference's engines (liblz4 decoder / hashlib) and the committed golden vect
 
 Bars: MD5 bit-exact; LZ4 frames decode bit-identically with three independent decoders (strict oracle
 decoder, liblz4's LZ4F_decompress = what lz4.frame.decompress calls at gateway_receiver.py:196, pyarrow);
-compression ratio >= 0.90 x the reference's on the compressible workload.
+compression ratio >= 0.95 x the reference's on the compressible workload (16 x 16 MiB); frames byte-identical to the
+sequential twin of the kernel's parse (tools/lz4_tile_model.c).
 """
 import hashlib
 
@@ -136,8 +137,34 @@ def test_long_matches_and_long_literal_runs(ctx):
         check_frame(f, d)
 
 
+def _twin_opts():
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from tools import tile_model
+
+    k = native.kernel_config()
+    return tile_model, tile_model.kernel_opts(k["lz4_entries"], k["tile"], k["max_step_log"])
+
+
+def test_frames_equal_sequential_twin(ctx):
+    """The warp-parallel parse is specified by a sequential program (tools/lz4_tile_model.c): same table rule, same tile
+    parse, same emission.  Frames must be byte-identical -- this pins every lane-level shortcut of the kernel (match.any
+    ordering, fused forward/backward compare, batched emission, stride doubling) to plain sequential semantics."""
+    tm, o = _twin_opts()
+    a = RNG.bytes(1000)
+    datas = [kinds(n)[k] for n in (13, 300, 4096, 65536, 65537, 200000) for k in ("zeros", "period7", "text", "half", "random")]
+    datas += [synth.silesia_like_chunk(40 + i, (1 << 20) + 777 * i) for i in range(6)]
+    datas += [a + bytes(60000) + a, RNG.bytes(300) + b"Q" * 65000, (RNG.bytes(70) * 1000)[:65536], RNG.bytes(40000) + synth.silesia_like_chunk(3, 90000)]
+    frames, _, _, _ = run_device(ctx, datas)
+    for i, (d, f) in enumerate(zip(datas, frames)):
+        want = tm.frame(d, o)
+        assert f == want, f"chunk {i} (len {len(d)}): GPU frame {len(f)} B != twin {len(want)} B"
+
+
 def test_ratio_parity_on_silesia_like(ctx):
-    datas = [synth.silesia_like_chunk(i, 16 << 20) for i in range(4)]
+    datas = [synth.silesia_like_chunk(i, 16 << 20) for i in range(16)]
     frames, digests, _, _ = run_device(ctx, datas)
     gpu = sum(map(len, frames))
     refsz = sum(len(ref.lz4f_compress(d)) for d in datas)
@@ -147,7 +174,7 @@ def test_ratio_parity_on_silesia_like(ctx):
     for d, f, dg in zip(datas, frames, digests):
         check_frame(f, d)
         assert dg == hashlib.md5(d).digest()
-    assert (total / gpu) >= 0.90 * (total / refsz)
+    assert (total / gpu) >= 0.95 * (total / refsz)
 
 
 def test_batch_of_8mib_chunks(ctx):

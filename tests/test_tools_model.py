@@ -1,59 +1,35 @@
-"""tools/lz4_window_model.c (the sequential CPU model of the GPU compressor's parse) must emit valid LZ4 blocks:
-each block is decoded with the strict oracle decoder wrapped in a minimal frame."""
-import ctypes
-import subprocess
+"""tools/lz4_tile_model.c (the sequential CPU twin of the GPU compressor's parse) must emit valid LZ4 and stay close to
+the reference's compression ratio: every frame is decoded with the strict oracle decoder and with liblz4."""
+import sys
 from pathlib import Path
 
 import numpy as np
 import pytest
 
 import oracle
+import oracle.reflib as ref
 from skyplane_b200 import synth
 
-ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from tools import tile_model as tm  # noqa: E402
 
 
-class Opts(ctypes.Structure):
-    _fields_ = [("hash_log", ctypes.c_int), ("window", ctypes.c_int), ("skip_trigger", ctypes.c_int), ("in_window", ctypes.c_int),
-                ("back_ext", ctypes.c_int)]
-
-
-@pytest.fixture(scope="module")
-def model():
-    so = ROOT / "tools" / "bin" / "liblz4model.so"
-    so.parent.mkdir(exist_ok=True)
-    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(so), str(ROOT / "tools" / "lz4_window_model.c")])
-    m = ctypes.CDLL(str(so))
-    m.model_compress_block.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.POINTER(Opts)]
-    m.model_compress_block.restype = ctypes.c_uint32
-    return m
-
-
-def frame_of_blocks(data: bytes, model, o: Opts) -> bytes:
-    hdr = bytes([0x04, 0x22, 0x4D, 0x18, 0x68, 0x40]) + len(data).to_bytes(8, "little")
-    hdr += bytes([(oracle.xxh32(hdr[4:]) >> 8) & 0xFF])
-    out = bytearray(hdr)
-    buf = ctypes.create_string_buffer(65536 + 16)
-    for pos in range(0, len(data), 65536):
-        blk = data[pos : pos + 65536]
-        c = model.model_compress_block(blk, len(blk), buf, ctypes.byref(o))
-        if c:
-            out += c.to_bytes(4, "little") + buf.raw[:c]
-        else:
-            out += (len(blk) | 0x80000000).to_bytes(4, "little") + blk
-    return bytes(out + bytes(4))
-
-
-@pytest.mark.parametrize("opts", [(12, 32, 6, 1, 1), (12, 32, 6, 1, 2), (11, 16, 6, 0, 0), (13, 64, 5, 1, 1)])
-def test_model_emits_valid_lz4(model, opts):
-    o = Opts(*opts)
+@pytest.mark.parametrize("opts", [tm.kernel_opts(), tm.kernel_opts(3072), tm.kernel_opts(2048, 256, 0), tm.Opts(4096, 8, 1024, 8, 1, 2, 1, 1)])
+def test_model_emits_valid_lz4(opts):
     rng = np.random.default_rng(3)
-    datas = [rng.bytes(n) for n in (1, 12, 13, 100, 65536)] + [bytes(70000), (b"abcdefg" * 20000)[:131073],
-                                                                synth.silesia_like_chunk(11, 300000), b"x" * 13 + rng.bytes(40) + b"x" * 200]
+    datas = [rng.bytes(n) for n in (1, 12, 13, 100, 65536)] + [bytes(70000), (b"abcdefg" * 20000)[:131073], b"",
+                                                                synth.silesia_like_chunk(11, 300000), b"x" * 13 + rng.bytes(40) + b"x" * 200,
+                                                                rng.bytes(40000) + synth.silesia_like_chunk(3, 90000)]
     for d in datas:
-        fr = frame_of_blocks(d, model, o)
+        fr = tm.frame(d, opts)
         assert oracle.lz4f_decode(fr, len(d)) == d
-    # the kernel's parse should stay within 10 % of the reference's ratio on the compressible set
-    d = synth.silesia_like_chunk(0, 4 << 20)
-    if opts[:2] == (12, 32):
-        assert len(d) / len(frame_of_blocks(d, model, o)) >= 0.90 * len(d) / len(oracle.lz4f_compress(d))
+        assert ref.lz4f_decompress(fr, len(d)) == d
+        assert len(fr) <= 15 + len(d) + 4 * ((len(d) + 65535) // 65536) + 4
+
+
+def test_kernel_parse_ratio_close_to_reference():
+    """The shipped parse (4096 entries, 5-byte hash, backward extension) keeps >= 0.96 x the reference's ratio."""
+    datas = [synth.silesia_like_chunk(i, 4 << 20) for i in range(2)]
+    ours = sum(len(tm.frame(d)) for d in datas)
+    refsz = sum(len(ref.lz4f_compress(d)) for d in datas)
+    assert refsz / ours >= 0.96
