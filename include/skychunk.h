@@ -67,7 +67,7 @@ SKY_API int sky_device_count(int *count);
  * unlike nvidia-smi -i); the host side maps it to the GPU's NUMA node before pinning staging memory. */
 SKY_API int sky_device_pci_bus_id(int device, char *buf, int len);
 /* Compile-time constants of the kernels in this build (tuning builds differ): what = 0 -> LZ4 match-table entries per
- * warp, 1 -> warps per CTA of the fused kernel, 2 -> probe slots per tile, 3 -> log2 of the largest probe stride.
+ * CTA, 1 -> warps per CTA of the fused kernel, 2 -> probe slots per segment, 3 -> log2 of the largest probe stride.
  * Unknown `what` returns 0.  Parity tests feed these to the sequential twin of the compressor (tools/lz4_tile_model.c). */
 SKY_API uint32_t sky_kernel_config(int what);
 

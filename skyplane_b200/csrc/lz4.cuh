@@ -226,14 +226,131 @@ __device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const ui
     return op;
 }
 
-// ---- cooperative forward extension: all lanes compare 4 bytes each per round, starting at match length `mlen`
-__device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src, uint32_t mpos, uint32_t mcand, uint32_t mlen,
-                                                uint32_t maxlen, unsigned lane) {
+// =====================================================================================================
+// CTA-per-block compressor.  One CTA owns one 64 KiB block at a time:
+//   * the block is brought into shared memory with ONE bulk async copy (TMA 1-D, cp.async.bulk + mbarrier);
+//   * warp 0 (the prober) walks the block segment by segment (kSegSlots probe slots each): hash 5 bytes, ONE
+//     shared-memory lookup of (pos16 | tag16) per slot, no byte of the candidate is read; lanes of a 32-slot group that
+//     hash alike are ordered with one match.any so the result equals sequential insertion.  Per segment it publishes a
+//     hit bit mask and the candidate offsets through a ring of shared-memory slots (mbarrier full / empty pairs);
+//   * the parser warps each take whole segments from the ring and parse them INDEPENDENTLY (cursor and anchor start at the
+//     segment start, matches are clipped to the segment end): per accepted match one warp-wide round compares 23 bytes
+//     ahead and 8 bytes behind -- verification, forward and backward extension in one ballot, all from shared memory --
+//     sequences are recorded one per lane and emitted 32 at a time into the segment's scratch area (L2-resident);
+//   * after a CTA barrier warp 0 strings the segments together (literals a segment leaves behind are carried into the
+//     next segment's first sequence), learns the block's frame offset from the OFF chain, and all warps write the block to
+//     its final place exactly once.
+// tools/lz4_tile_model.c is the sequential twin of exactly these rules (frames are byte-identical, tested).
+#ifndef SKY_COOP_LIT
+#define SKY_COOP_LIT 16
+#endif
+#ifndef SKY_MAX_STEP_LOG
+#define SKY_MAX_STEP_LOG 4
+#endif
+#ifndef SKY_SEG_GROUPS
+#define SKY_SEG_GROUPS 32
+#endif
+constexpr uint32_t kCoopLit = SKY_COOP_LIT;          // literal runs at least this long are copied by the whole warp
+constexpr uint32_t kMaxStepLog = SKY_MAX_STEP_LOG;   // probe stride doubles after a segment without a hit, up to 1 << this
+constexpr int kSegGroups = SKY_SEG_GROUPS;           // a segment = this many warp-wide groups of probe slots (<= 32)
+constexpr uint32_t kSegSlots = kSegGroups * 32;
+constexpr uint32_t kMaxSegs = kBlock / kSegSlots;    // most segments a block can have (stride 1 throughout)
+constexpr uint32_t kSegPad = 80;                     // scratch slack per segment: a segment's sequences can outgrow it by < 70 B
+constexpr uint32_t kScratchBytes = kBlock + kMaxSegs * kSegPad + 1024;  // per-CTA compressed-segment scratch (global, L2)
+static_assert(kSegGroups >= 1 && kSegGroups <= 32, "SKY_SEG_GROUPS must be 1..32");
+
+// ring slot: what the prober hands a parser for one segment
+struct SegSlot {
+    uint16_t offs[kSegSlots];   // slot i: position - candidate position (valid where the hit bit is set)
+    uint32_t masks[32];         // group g: hit bits of its 32 slots (groups >= kSegGroups: 0)
+    uint32_t seg_pos, slog, sidx, pad;
+};
+// what a parser leaves behind for one segment
+struct SegRec {
+    uint32_t seg_pos;
+    uint32_t lead_ml;   // first sequence: literals from the segment start | match length << 16 (0 = no match in the segment)
+    uint32_t off_t;     // first sequence's offset | trailing literal bytes << 16
+    uint32_t mbytes;    // bytes of the 2nd.. sequences in the segment's scratch area
+};
+struct SegPlan {
+    uint32_t foff, moff;  // where the first sequence / the rest go, relative to the block's first data byte
+    uint32_t fll, pad;    // first sequence's full literal length (carry + lead)
+};
+
+// ---- mbarrier / bulk-copy primitives (shared::cta) -----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Explicit shared-state-space accessors on 32-bit shared addresses: the hot loops must compile to LDS / STS with 32-bit
+// address arithmetic, whatever the compiler can or cannot infer about a pointer's address space.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// try_wait with a suspend-time hint (ns): the waiting warp is parked by the hardware instead of spinning through the
+// scheduler -- a spinning parser would take issue slots from the prober it is waiting for
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {}
+}
+// global -> shared bulk async copy (TMA 1-D): bytes multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t div255(uint32_t x) { return (x * 0x8081u) >> 23; }  // exact for x < 65536
+__device__ __forceinline__ uint32_t seq_bytes_fast(uint32_t ll, uint32_t ml) {           // ll, ml < 65536
+    uint32_t s = 1 + ll + (ll >= 15 ? div255(ll - 15) + 1 : 0);
+    if (ml) s += 2 + (ml >= 19 ? div255(ml - 19) + 1 : 0);
+    return s;
+}
+// unaligned little-endian 32-bit read from the shared-memory copy of the block (in_s = its 32-bit shared address)
+__device__ __forceinline__ uint32_t load32s(uint32_t in_s, uint32_t pos) {
+    const uint32_t a = in_s + (pos & ~3u);
+    return __funnelshift_r(lds32(a), lds32(a + 4), (pos & 3u) * 8u);
+}
+
+// ---- cooperative forward extension in shared memory: all lanes compare 4 bytes each per round
+__device__ __forceinline__ uint32_t extend_coop_s(uint32_t in32, uint32_t mpos, uint32_t mcand, uint32_t mlen, uint32_t maxlen,
+                                                  unsigned lane) {
     for (;;) {
         const uint32_t o = mlen + lane * 4;
         uint32_t cnt = 0;
         if (o < maxlen) {
-            const uint32_t x = load32(src, mpos + o) ^ load32(src, mcand + o);
+            const uint32_t x = load32s(in32, mpos + o) ^ load32s(in32, mcand + o);
             cnt = x ? (uint32_t)(__ffs(x) - 1) >> 3 : 4u;
             cnt = min(cnt, maxlen - o);
         }
@@ -247,28 +364,13 @@ __device__ __forceinline__ uint32_t extend_coop(const uint8_t *__restrict__ src,
     }
 }
 
-#ifndef SKY_COOP_LIT
-#define SKY_COOP_LIT 16
-#endif
-#ifndef SKY_MAX_STEP_LOG
-#define SKY_MAX_STEP_LOG 4
-#endif
-constexpr uint32_t kCoopLit = SKY_COOP_LIT;          // literal runs at least this long are copied by the whole warp
-constexpr uint32_t kMaxStepLog = SKY_MAX_STEP_LOG;   // probe stride doubles after a tile without a hit, up to 1 << this
-constexpr int kGroups = 8;                           // a tile = 8 warp-wide groups = 256 probe slots
-constexpr uint32_t kTile = kGroups * 32;
-constexpr uint32_t kOffsBytes = kTile * 2;           // per-warp u16 offsets of the current tile's slots
-constexpr uint32_t kLz4AreaBytes = kTableBytes + kOffsBytes;
-constexpr uint32_t kScratchBytes = kBlock + 1024;    // per-warp compressed-block scratch (output can overshoot L by < 300 B)
-
-__device__ __forceinline__ uint32_t div255(uint32_t x) { return (x * 0x8081u) >> 23; }  // exact for x < 65536
-
 // ---- emission of up to 32 recorded sequences, one per lane ------------------------------------------
-// q0 = literal length | match length << 16, q1 = literal start | offset << 16 (lane k = k-th sequence).
-// Sizes go through a warp scan; every lane writes its own token, length bytes, literals (runs >= kCoopLit: one warp
-// copy each), offset and match-length bytes.  Returns the new output cursor.  Not inlined: called from two places.
-__device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t op, const uint8_t *__restrict__ src, uint32_t q0,
-                                            uint32_t q1, uint32_t nseq, unsigned lane) {
+// q0 = literal length | match length << 16, q1 = literal start | offset << 16 (lane k = k-th sequence).  Literals come
+// from the shared-memory copy of the block, output goes to the segment's scratch area.  Sizes go through a warp scan; every
+// lane writes its own token, length bytes, literals (runs >= kCoopLit: one warp copy each), offset and match-length bytes.
+__device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t op, const uint8_t *in, uint32_t q0, uint32_t q1,
+                                            uint32_t nseq, unsigned lane) {
+    const uint32_t in32 = smem_u32(in);
     const bool act = lane < nseq;
     const uint32_t ll = q0 & 0xffffu, ml = q0 >> 16, lit = q1 & 0xffffu, off = q1 >> 16;
     const uint32_t mcode = ml - kMinMatch;
@@ -294,15 +396,15 @@ __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t 
         if (ll < kCoopLit) {
             uint32_t k = 0;
             for (; k + 4 <= ll; k += 4) {  // 4 literal bytes per round: one unaligned read, four byte stores
-                const uint32_t w = load32(src, lit + k);
+                const uint32_t w = load32s(in32, lit + k);
                 out[o + k] = (uint8_t)w;
                 out[o + k + 1] = (uint8_t)(w >> 8);
                 out[o + k + 2] = (uint8_t)(w >> 16);
                 out[o + k + 3] = (uint8_t)(w >> 24);
             }
             const uint32_t rem = ll - k;
-            if (rem) {  // (literals of a match sequence end >= 12 bytes before the block end: the word read is in range)
-                const uint32_t w = load32(src, lit + k);
+            if (rem) {
+                const uint32_t w = load32s(in32, lit + k);
                 out[o + k] = (uint8_t)w;
                 if (rem > 1) out[o + k + 1] = (uint8_t)(w >> 8);
                 if (rem > 2) out[o + k + 2] = (uint8_t)(w >> 16);
@@ -319,144 +421,153 @@ __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t 
     }
     __syncwarp();
     unsigned big = __ballot_sync(kFull, act && ll >= kCoopLit);
-    while (big) {  // long literal runs: one warp-wide copy each
+    while (big) {  // long literal runs: one warp-wide copy each (generic loads: the source is shared memory)
         const int l = __ffs(big) - 1;
         big &= big - 1;
-        warp_copy(out + __shfl_sync(kFull, lit_o, l), src + __shfl_sync(kFull, lit, l), __shfl_sync(kFull, ll, l), lane);
+        warp_copy(out + __shfl_sync(kFull, lit_o, l), in + __shfl_sync(kFull, lit, l), __shfl_sync(kFull, ll, l), lane);
     }
     return op + total;
 }
 
-// ---- the block compressor -------------------------------------------------------------------------
-// src: block start in the chunk (16-byte aligned), L: block length (1..65536), out: this warp's scratch (kScratchBytes),
-// tab: this warp's shared-memory area (kLz4AreaBytes: match table, then the tile's slot offsets).
-// Returns the compressed size (1..L-1), or 0 if the block does not shrink (caller stores it raw).
-//
-// The block is parsed tile by tile (kTile probe slots at stride 1 << slog), three decoupled phases per tile, each with
-// all 32 lanes busy (tools/lz4_tile_model.c is the sequential twin of exactly these rules):
-//   pass 1  every slot: read 5 bytes, hash, ONE shared-memory lookup of (pos16 | tag16); a hit is a tag match, no byte of
-//           the candidate is read.  Lanes of a group that hash alike are ordered with one match.any so the result equals
-//           sequential insertion (nearest lower lane = most recent occurrence; the highest lane stores).
-//   pass 2  greedy parse over the hit bit masks: per accepted match one warp-wide round compares 24 bytes ahead and 8
-//           bytes behind (coalesced byte loads) -- verification, forward and backward extension in one ballot; longer
-//           matches continue 128 bytes per round.  Sequences are recorded one per lane.
-//   pass 3  every 32 sequences: flush_seqs (scan of sizes, lane-parallel emission).
-__device__ __forceinline__ uint32_t lz4_compress_block(const uint8_t *__restrict__ src, uint32_t L, uint8_t *__restrict__ out,
-                                                      uint32_t *tab, unsigned lane) {
-    {   // clear the table: 32 lanes x 16 B per round; entry 0 = (position 0, tag 0) doubles as "empty"
-        uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll 4
-        for (uint32_t k = lane; k < kEntries / 4; k += 32) t4[k] = z;
-    }
-    uint16_t *offs = reinterpret_cast<uint16_t *>(tab + kEntries);
-    __syncwarp();
-
-    uint32_t anchor = 0, cur = 0, op = 0, nseq = 0, q0 = 0, q1 = 0;
-    const uint32_t limit = L - 1;  // accept only csize <= L-1 (LZ4F_makeBlock passes dstCapacity = srcSize-1)
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    if (L >= kMfLimit + 1) {
-        const uint32_t mflimit = L - kMfLimit;          // last position a match may start at
-        const uint32_t matchlimit = L - kLastLiterals;  // matches end at or before this
-        const uint32_t *W = reinterpret_cast<const uint32_t *>(src);
-        const int dl = lane < 24 ? (int)lane : 23 - (int)lane;  // byte this lane compares: +0..+23 ahead, -1..-8 behind
-        uint32_t tb = 0, slog = 0;
-        while (tb <= mflimit) {
-            const uint32_t span = kTile << slog;
-            if (lane == 0) {  // pull the tile after next towards L2 (the MD5 lanes of the chunk share it)
-                const uint32_t pf = (tb + 2 * span) & ~15u;
-                if (pf < L) l2_prefetch_bulk(src + pf, min(span, ((L - pf) + 15u) & ~15u));
-            }
-            // ---- pass 1
-            uint32_t mymask = 0;
+// ---- prober: one segment.  Writes the segment's hit masks and candidate offsets; returns whether any slot hit.
+// Software-pipelined 8 groups at a time: everything that does not depend on the table (input words, hash, the match.any
+// ordering of the lanes, the in-group candidate) is computed for all 8 groups first; then the 8 table lookups and stores
+// are issued back to back (the LSU keeps a warp's shared-memory accesses in order, so group k+1's lookup sees group k's
+// store without waiting for group k's lookup to return); only then are the lookups' results consumed.
+// Slots past the last probe position (p > mflimit, only at the very end of a block, always the highest lanes) hash a
+// clamped position and are masked out of the hits; they may win a table store, which no later lookup can observe.
+__device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (0xffffffff for 0): one FLO
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ bool probe_segment(uint32_t in_s, uint32_t tab_s, uint32_t offs_s, uint32_t masks_s, uint32_t seg_pos,
+                                              uint32_t slog, uint32_t mflimit, unsigned lane) {
+    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~((2u << lane) - 1u);
+    const uint32_t pstep = 32u << slog;
+    uint32_t p = seg_pos + (lane << slog);
+    // p & 3 is the same for every group of the segment (p advances by a multiple of 32): byte selectors are loop-invariant
+    const uint32_t selv = 0x3210u + 0x1111u * (p & 3u), selb = 0x4440u | (p & 3u);
+    uint32_t offs_l = offs_s + lane * 2u, anyhit = 0;
+#pragma unroll 1
+    for (int g0 = 0; g0 < kSegGroups; g0 += 8) {
+        uint32_t idx[8], mine[8], e[8], e_near[8];
+        bool valid[8], has_lower[8], stores[8];
 #pragma unroll
-            for (int g = 0; g < kGroups; g++) {
-                const uint32_t p = tb + ((uint32_t)(g * 32 + lane) << slog);
-                const bool valid = p <= mflimit;
-                uint32_t mine = 0, idx = 0xffff0000u | lane, e = 0;
-                if (valid) {
-                    const uint32_t w0 = __ldg(W + (p >> 2)), w1 = __ldg(W + (p >> 2) + 1);
-                    const uint32_t sh = (p & 3u) * 8u;
-                    uint32_t hf = __funnelshift_r(w0, w1, sh) * 2654435761u;
-                    hf = ((w1 >> sh) & 0xffu) * 0x85EBCA6Bu + hf;  // fifth byte
-                    idx = __umulhi(hf, kEntries);
-                    mine = __byte_perm(p, hf, 0x6510);  // pos16 | hash bytes 1-2 as the tag
-                    e = tab[idx];
-                }
-                const unsigned grp = __match_any_sync(kFull, idx);
-                const unsigned lower = grp & lt_mask;
-                const uint32_t e_near = __shfl_sync(kFull, mine, lower ? 31 - __clz(lower) : 0);
-                if (lower) e = e_near;  // a lower lane of this group filled the slot more recently than the table knows
-                const uint32_t x = e ^ mine;
-                const unsigned hits = __ballot_sync(kFull, valid && x < 65536u && x != 0u);  // (also: table reads before writes)
-                if ((int)lane == g) mymask = hits;
-                offs[g * 32 + lane] = (uint16_t)(mine - e);
-                if (valid && (grp >> lane) == 1u) tab[idx] = mine;
-                __syncwarp();
-            }
-            // ---- pass 2
-            unsigned nz = __ballot_sync(kFull, mymask != 0u);
-            const bool anyhit = nz != 0u;
-            bool accepted = false;
-            uint32_t m = 0, gbase = 0;
-            for (;;) {
-                if (m == 0) {
-                    if (nz == 0) break;
-                    const int g = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    m = __shfl_sync(kFull, mymask, g);
-                    gbase = tb + ((uint32_t)(g * 32) << slog);
-                }
-                if (cur > gbase) {  // drop the slots the cursor has passed
-                    m &= __funnelshift_lc(0u, 0xffffffffu, (cur - gbase + (1u << slog) - 1u) >> slog);
-                    if (m == 0) continue;
-                }
-                const uint32_t bit = (uint32_t)__ffs(m) - 1u;
-                m &= m - 1;
-                uint32_t pos = gbase + (bit << slog);
-                const uint32_t off = offs[((gbase - tb) >> slog) + bit];
-                const uint32_t cand = pos - off;
-                const uint32_t maxlen = matchlimit - pos;  // >= 7
-                const uint32_t room = min(min(pos - anchor, cand), 8u);
-                bool ok = false;
-                if (lane < 24 ? lane < maxlen : lane - 24 < room) ok = src[(int)pos + dl] == src[(int)cand + dl];
-                const unsigned eq = __ballot_sync(kFull, ok);
-                const int f = __ffs(~eq & 0xffffffu);
-                uint32_t mlen = f ? (uint32_t)(f - 1) : 24u;
-                if (mlen < kMinMatch) continue;  // tag collision (or only 4 of the 5 hashed bytes... still a valid match if >= 4)
-                if (mlen == 24u && maxlen > 24u) mlen = extend_coop(src, pos, cand, 24u, maxlen, lane);
-                const uint32_t back = (uint32_t)__ffs(~(eq >> 24)) - 1u;
-                pos -= back;
-                mlen += back;
-                const uint32_t r0 = (pos - anchor) | (mlen << 16), r1 = anchor | (off << 16);
-                if (lane == nseq) {
-                    q0 = r0;
-                    q1 = r1;
-                }
-                nseq++;
-                anchor = cur = pos + mlen;
-                accepted = true;
-                if (nseq == 32) {
-                    op = flush_seqs(out, op, src, q0, q1, 32, lane);
-                    nseq = 0;
-                    if (op + 1 + kLastLiterals > limit) return 0;  // cannot end up smaller than the input
-                }
-            }
-            tb = max(tb + span, cur);
-            if (accepted) slog = 0;
-            else if (!anyhit && slog < kMaxStepLog) slog++;
+        for (int k = 0; k < 8; k++) {
+            valid[k] = p <= mflimit;
+            const uint32_t pc = min(p, mflimit);
+            const uint32_t a = in_s + (pc & ~3u);
+            const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+            uint32_t hf = __byte_perm(w0, w1, selv) * 2654435761u;
+            hf = __byte_perm(w1, 0u, selb) * 0x85EBCA6Bu + hf;  // fifth byte
+            idx[k] = __umulhi(hf, kEntries) * 4u;               // byte offset of the table entry
+            mine[k] = __byte_perm(p, hf, 0x6510);               // pos16 | hash bytes 1-2 as the tag
+            p += pstep;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const unsigned grp = __match_any_sync(kFull, idx[k]);
+            const unsigned lower = grp & lt_mask;
+            has_lower[k] = lower != 0u;
+            e_near[k] = __shfl_sync(kFull, mine[k], bfind(lower));  // nearest lower lane = most recent occurrence (unused if none)
+            stores[k] = (grp & gt_mask) == 0u;                      // the highest lane of the group stores
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            e[k] = lds32(tab_s + idx[k]);
+            __syncwarp();  // (orders the lanes' table reads of this group before its writes)
+            if (stores[k]) sts32(tab_s + idx[k], mine[k]);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t ek = has_lower[k] ? e_near[k] : e[k];  // a lower lane filled the slot more recently than the table knows
+            const uint32_t x = ek ^ mine[k];
+            const unsigned hits = __ballot_sync(kFull, valid[k] && (x - 1u) < 65535u);  // tag equal, position differs
+            anyhit |= hits;
+            if (lane == 0) sts32(masks_s + (uint32_t)(g0 + k) * 4u, hits);
+            sts16(offs_l + (uint32_t)k * 64u, mine[k] - ek);
+        }
+        offs_l += 8u * 64u;
     }
-    if (nseq) {
-        op = flush_seqs(out, op, src, q0, q1, nseq, lane);
-        if (op + 1 + kLastLiterals > limit) return 0;
+    return anyhit != 0u;
+}
+
+// ---- parser: one segment.  in = shared-memory copy of the block, scr = this segment's scratch area.
+__device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot *slot, uint8_t *__restrict__ scr, uint32_t L,
+                                                unsigned lane) {
+    const uint32_t in32 = smem_u32(in), offs_s = smem_u32(slot->offs);
+    const uint32_t seg_pos = slot->seg_pos, slog = slot->slog;
+    const uint32_t mymask = slot->masks[lane];
+    const uint32_t mflimit = L - kMfLimit, matchlimit = L - kLastLiterals;
+    const uint32_t seg_lim = seg_pos + (kSegSlots << slog);
+    const uint32_t mlim = min(matchlimit, seg_lim);                 // matches end at or before this
+    const uint32_t seg_end = seg_lim > mflimit ? L : seg_lim;      // the last segment owns the block's tail
+    const uint32_t round_up = (1u << slog) - 1u;
+    const int dl = lane < 23 ? (int)lane : (int)lane - 32;  // byte this lane compares: +0..+22 ahead, -1..-8 behind (lane 31 = -1)
+    const uint32_t jrel = lane < 23 ? lane : 31u - lane;    // its distance from the match start
+    uint32_t anchor = seg_pos, cur = seg_pos, nseq = 0, q0 = 0, q1 = 0, mbytes = 0;
+    uint32_t first_lead_ml = 0, first_off = 0;
+    bool first = true;
+    unsigned nz = __ballot_sync(kFull, mymask != 0u);
+    uint32_t m = 0, gbase = 0, sbase = 0;
+    for (;;) {
+        if (m == 0) {
+            if (nz == 0) break;
+            const int g = __ffs(nz) - 1;
+            nz &= nz - 1;
+            m = __shfl_sync(kFull, mymask, g);
+            sbase = (uint32_t)g * 32u;
+            gbase = seg_pos + (sbase << slog);
+            m &= __funnelshift_lc(0u, 0xffffffffu, (max(cur, gbase) - gbase + round_up) >> slog);  // slots the cursor has passed
+            if (m == 0) continue;
+        }
+        const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+        uint32_t pos = gbase + (bit << slog);
+        if (pos >= mlim) break;  // nothing from here on can hold a match
+        const uint32_t off = lds16(offs_s + (sbase + bit) * 2u);
+        const uint32_t cand = pos - off;
+        const uint32_t maxlen = mlim - pos;
+        const uint32_t room = min(min(pos - anchor, cand), 8u);
+        bool ok = false;
+        if (jrel < (lane < 23 ? maxlen : room)) ok = lds8(in32 + pos + (uint32_t)dl) == lds8(in32 + cand + (uint32_t)dl);
+        const unsigned z = ~__ballot_sync(kFull, ok) | 0x00800000u;  // bit 23 = stop bit of the forward scan
+        uint32_t mlen = (uint32_t)__ffs(z) - 1u;                   // 0..23
+        if (mlen == 23u && maxlen > 23u) mlen = extend_coop_s(in32, pos, cand, 23u, maxlen, lane);
+        if (mlen < kMinMatch) {  // tag collision
+            m &= m - 1;
+            continue;
+        }
+        const uint32_t back = (uint32_t)__clz(z);  // 0..8 (lane 31 = byte -1)
+        const uint32_t end = pos + mlen;
+        pos -= back;
+        mlen += back;
+        if (first) {
+            first = false;
+            first_lead_ml = (pos - seg_pos) | (mlen << 16);
+            first_off = off;
+        } else {
+            const uint32_t r0 = (pos - anchor) | (mlen << 16), r1 = anchor | (off << 16);
+            if (lane == nseq) {
+                q0 = r0;
+                q1 = r1;
+            }
+            if (++nseq == 32) {
+                mbytes = flush_seqs(scr, mbytes, in, q0, q1, 32, lane);
+                nseq = 0;
+            }
+        }
+        anchor = cur = end;
+        m &= __funnelshift_lc(0u, 0xffffffffu, (cur - gbase + round_up) >> slog);
     }
-    // last literals
-    const uint32_t last = L - anchor;
-    if (op + seq_bytes(last, 0) > limit) return 0;
-    op = emit_seq(out, op, src, anchor, last, 0, 0, lane);
-    return op;
+    if (nseq) mbytes = flush_seqs(scr, mbytes, in, q0, q1, nseq, lane);
+    SegRec r;
+    r.seg_pos = seg_pos;
+    r.lead_ml = first_lead_ml;
+    r.off_t = first_off | ((seg_end - anchor) << 16);
+    r.mbytes = mbytes;
+    return r;
 }
 
 }  // namespace sky

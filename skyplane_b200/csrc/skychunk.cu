@@ -43,20 +43,48 @@
 
 namespace sky {
 
-#ifndef SKY_WARPS
-#define SKY_WARPS 13
+#ifndef SKY_PARSERS
+#define SKY_PARSERS 10
 #endif
-constexpr int kWarps = SKY_WARPS;
+constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
+constexpr int kWarps = 1 + kParsers;      // + the prober (warp 0)
 constexpr int kThreads = kWarps * 32;
-constexpr int kMd5WarpsPerCta = 4;  // warps 0..3 (one per SM sub-partition) may host MD5 groups
+constexpr int kRing = kParsers + 3;       // segment slots between the prober and the parsers
+constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
-// every warp owns one area: LZ4 match table + tile offsets, or (warps 0..3, while hosting a digest group) the MD5 ring
-constexpr uint32_t kAreaBytes = kLz4AreaBytes > kRingBytes ? kLz4AreaBytes : kRingBytes;
-constexpr uint32_t kSmemBytes = kWarps * kAreaBytes;
-static_assert(kSmemBytes <= 232448, "shared memory per CTA exceeds 227 KiB: lower SKY_WARPS or SKY_LZ4_ENTRIES");
-static_assert(kEntries % 128 == 0, "SKY_LZ4_ENTRIES must be a multiple of 128");
+constexpr int kCtasPerSm = 2;             // fused kernel: 2 x ~110 KiB of shared memory per SM
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
+
+// ---- shared-memory layout of the fused kernel (dynamic, 128-byte aligned base) -------------------------
+struct BlockDesc {            // written by the prober's lane 0, read by every warp after the block-start barrier
+    const uint8_t *src;       // block start in the chunk (16-byte aligned)
+    uint8_t *dst;             // chunk's frame region
+    uint32_t c, j, L, last;   // chunk, block index, block length, 1 = last block of the chunk
+    uint32_t valid, pad;
+};
+struct Ctl {
+    uint64_t in_full;               // bulk copy of the block has landed
+    uint64_t full[kRing], empty[kRing];
+    BlockDesc desc[2];              // by block-iteration parity
+    uint32_t claim;                 // next segment sequence number a parser may take (runs across blocks)
+    volatile uint32_t block_end_seq;  // sequence number after the current block's last segment (0xffffffff while probing)
+    volatile uint32_t nseg;
+    uint32_t csize, raw, last_lits, tail_off;   // plan results: compressed size, stored?, final literal run and where it goes
+    uint32_t data_lo, data_hi;                  // frame offset of the block's first data byte
+};
+constexpr uint32_t kInBytes = kBlock + 128;    // + slack: unaligned 4-byte reads may touch the word after the last byte
+constexpr uint32_t kInOff = 0;
+constexpr uint32_t kTabOff = kInOff + kInBytes;
+constexpr uint32_t kRingOff = kTabOff + kTableBytes;
+constexpr uint32_t kRecOff = kRingOff + kRing * (uint32_t)sizeof(SegSlot);
+constexpr uint32_t kPlanOff = kRecOff + kMaxSegs * (uint32_t)sizeof(SegRec);
+constexpr uint32_t kCtlOff = kPlanOff + kMaxSegs * (uint32_t)sizeof(SegPlan);
+constexpr uint32_t kSmemBytes = (kCtlOff + (uint32_t)sizeof(Ctl) + 127u) & ~127u;
+static_assert(kSmemBytes <= 232448 / 2 - 1024, "two CTAs per SM need <= 112.5 KiB each: lower SKY_PARSERS or SKY_LZ4_ENTRIES");
+static_assert(kEntries % 128 == 0, "SKY_LZ4_ENTRIES must be a multiple of 128");
+static_assert(kMd5WarpsPerCta * kRingBytes <= kInBytes, "the MD5 rings live in the block buffer of a digest CTA");
+static_assert(sizeof(SegSlot) % 16 == 0 && sizeof(SegRec) == 16 && sizeof(SegPlan) == 16, "layout");
 
 struct ChunkDesc {
     const uint8_t *src;  // 16-byte aligned
@@ -74,9 +102,10 @@ struct Params {
     uint64_t *out_len;          // per chunk frame length
     uint8_t *md5_out;           // 16 bytes per chunk
     uint32_t *counters;         // [0] = LZ4 work counter
-    uint8_t *scratch;           // kScratchBytes per warp of the grid: where a block is compressed before its frame offset is known
+    uint8_t *scratch;           // kScratchBytes per CTA: where a block's segments are compressed before its frame offset is known
     uint32_t n_chunks;
     uint32_t n_groups;
+    uint32_t n_md5_ctas;        // CTAs 0..n_md5_ctas-1 digest (4 groups each at a time) before they compress
     uint32_t rows;  // max(1, max nblk)
     uint32_t flags;
 };
@@ -103,120 +132,295 @@ __device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t *p) {
     return v;
 }
 
-// One LZ4 work item: block j of chunk c.  The block is compressed into this warp's private scratch (L2-resident, reused
-// block after block); once the OFF chain says where the block starts in the frame it is written there exactly once
-// (16-byte streaming stores), or -- stored raw -- copied straight from the input.
-__device__ __forceinline__ void lz4_work(const Params &p, uint32_t c, uint32_t j, uint32_t *tab, uint8_t *scratch, unsigned lane,
-                                         bool pace) {
-    const ChunkDesc cd = p.chunks[c];
-    if (cd.nblk == 0) {
-        if (j == 0 && lane == 0) {  // empty chunk: 7-byte header + EndMark
-            const uint32_t h = write_frame_header(cd.dst, 0);
-            cd.dst[h] = cd.dst[h + 1] = cd.dst[h + 2] = cd.dst[h + 3] = 0;
-            p.out_len[c] = h + 4;
+// Prober lane 0: claim the next block that has LZ4 work (empty chunks are finished on the spot), wait until the chunk's
+// MD5 lanes are close (so the block is read from HBM once), and describe it to the CTA.
+__device__ __forceinline__ void claim_block(const Params &p, BlockDesc *d, bool pace) {
+    const uint32_t total = p.rows * p.n_chunks;
+    for (;;) {
+        const uint32_t w = atomicAdd(p.counters, 1u);
+        if (w >= total) {
+            d->valid = 0;
+            return;
         }
-        return;
-    }
-    if (j >= cd.nblk) return;
-
-    const uint64_t boff = (uint64_t)j * kBlock;
-    const uint32_t L = (uint32_t)min((uint64_t)kBlock, cd.len - boff);
-    const uint8_t *src = cd.src + boff;
-    if (lane == 0) {
+        const uint32_t c = w % p.n_chunks, j = w / p.n_chunks;  // row-major: block row j of every chunk, then row j+1
+        const ChunkDesc cd = p.chunks[c];
+        if (cd.nblk == 0) {
+            if (j == 0) {  // empty chunk: 7-byte header + EndMark
+                const uint32_t h = write_frame_header(cd.dst, 0);
+                cd.dst[h] = cd.dst[h + 1] = cd.dst[h + 2] = cd.dst[h + 3] = 0;
+                p.out_len[c] = h + 4;
+            }
+            continue;
+        }
+        if (j >= cd.nblk) continue;
         if (pace) {
-            // stay at most one 64 KiB row ahead of the MD5 lanes of this chunk (only while they are running)
+            // stay at most one 64 KiB row ahead of the MD5 lanes of this chunk (only while they are running); the last
+            // rows may run up to kTailLead rows ahead so the compressor's own latency for the final row overlaps the
+            // digest's last rows instead of trailing them
             const uint32_t *pw = p.md5_progress + cd.group;
-            // the last rows of a chunk may run up to kTailLead rows ahead, so the compressor's own latency for the
-            // final row (milliseconds on compressible data) overlaps the digest's last rows instead of trailing them
             constexpr uint32_t kTailLead = 8;
             const uint32_t lead = (cd.nblk - j <= kTailLead) ? kTailLead : 0;
             unsigned ns = 64;
             for (;;) {
                 const uint32_t pr = ld_relaxed32(pw);
-                // pr: 0 = digest not started, 0xffffffff = digest finished, else 1 + rows consumed (64-bit compare:
-                // pr + lead must not wrap when the digest has already finished)
+                // pr: 0 = digest not started, 0xffffffff = finished, else 1 + rows consumed (64-bit compare: no wrap)
                 if (pr == 0 || (uint64_t)j + 1 <= (uint64_t)pr + lead) break;
                 __nanosleep(ns);
                 if (ns < 4096) ns <<= 1;
             }
         }
-        l2_prefetch_bulk(src, min(2048u, (L + 15u) & ~15u));  // the compressor prefetches the rest tile by tile
+        const uint64_t boff = (uint64_t)j * kBlock;
+        d->src = cd.src + boff;
+        d->dst = cd.dst;
+        d->c = c;
+        d->j = j;
+        d->L = (uint32_t)min((uint64_t)kBlock, cd.len - boff);
+        d->last = (j + 1 == cd.nblk);
+        d->valid = 1;
         if (j == 0) write_frame_header(cd.dst, cd.len);
-    }
-    __syncwarp();
-
-    const uint32_t csize = lz4_compress_block(src, L, scratch, tab, lane);
-    __syncwarp();
-
-    // OFF chain: learn where this block starts, tell the successor at once
-    uint64_t st = 0;
-    if (lane == 0) {
-        uint64_t *cw = p.chain + c;
-        unsigned ns = 128;
-        while (((st = ld_acquire(cw)) >> kOffBits) != j) {
-            __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
-        }
-    }
-    st = __shfl_sync(kFull, st, 0);
-    const uint64_t off = st & kOffMask;
-    const uint32_t bsize = csize ? csize : L;
-    const uint32_t hword = csize ? csize : (L | 0x80000000u);
-    const uint64_t end = off + 4 + bsize;
-    const bool last = (j + 1 == cd.nblk);
-    if (lane == 0 && !last) st_release(p.chain + c, ((uint64_t)(j + 1) << kOffBits) | end);
-    uint8_t *hdr = cd.dst + off;
-    if (csize) warp_copy_stream<false>(hdr + 4, scratch, csize, lane);
-    else warp_copy_stream<true>(hdr + 4, src, L, lane);  // stored block: straight from the input
-    if (lane < 4) hdr[lane] = (uint8_t)(hword >> (8 * lane));
-    if (last) {
-        if (lane < 4) cd.dst[end + lane] = 0;  // EndMark
-        if (lane == 0) p.out_len[c] = end + 4;
+        return;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) sky_fused_kernel(const Params p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+// Fused LZ4-frame + MD5 kernel.  Grid = 2 CTAs per SM, kWarps warps each.
+//   digest CTAs (blockIdx < n_md5_ctas): warps 0..3 each carry one MD5 group (32 chunks, lane = chunk, md5.cuh) at a time;
+//       when the groups are done the CTA joins the compressors.
+//   compressor CTAs: one 64 KiB block at a time -- bulk-load it into shared memory, warp 0 probes, warps 1.. parse
+//       (lz4.cuh), warp 0 plans the block's layout and takes its frame offset from the OFF chain, all warps write it out.
+// OFF chain (per chunk): (next block index << 40) | frame offset of that block -- a prefix sum handed from block j-1 to
+// block j as soon as j-1 knows its compressed size.  Waiting is deadlock-free: a CTA only waits on lower-numbered work
+// items, all of which were claimed earlier by running CTAs.
+__global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *my = smem + warp * kAreaBytes;
+    uint8_t *in = smem + kInOff;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(smem + kTabOff);
+    SegSlot *ring = reinterpret_cast<SegSlot *>(smem + kRingOff);
+    SegRec *recs = reinterpret_cast<SegRec *>(smem + kRecOff);
+    SegPlan *plans = reinterpret_cast<SegPlan *>(smem + kPlanOff);
+    Ctl *ctl = reinterpret_cast<Ctl *>(smem + kCtlOff);
 
     const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
-    const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
-
-    if (do_md5 && warp < kMd5WarpsPerCta) {
-        for (uint32_t g = warp * gridDim.x + blockIdx.x; g < p.n_groups; g += md5_slots) {
-            const uint32_t c = p.md5_order[g * 32 + lane];
-            const bool active = c != 0xffffffffu;
-            const uint8_t *src = nullptr;
-            uint64_t len = 0;
-            if (active) {
-                src = p.chunks[c].src;
-                len = p.chunks[c].len;
-            }
-            volatile uint32_t *prog = p.md5_progress + g;
-            if (lane == 0) *prog = 1u;  // started, 0 rows consumed
-            md5_warp(reinterpret_cast<uint32_t *>(my), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16, lane, prog);
-            if (lane == 0) *prog = 0xffffffffu;
-            __syncwarp();
+    if (threadIdx.x == 0) {
+        mbar_init(&ctl->in_full, 1);
+        for (int i = 0; i < kRing; i++) {
+            mbar_init(&ctl->full[i], 1);
+            mbar_init(&ctl->empty[i], 1);
         }
+        ctl->claim = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (do_md5 && blockIdx.x < p.n_md5_ctas) {
+        if (warp < kMd5WarpsPerCta) {
+            for (uint32_t g = warp * p.n_md5_ctas + blockIdx.x; g < p.n_groups; g += p.n_md5_ctas * kMd5WarpsPerCta) {
+                const uint32_t c = p.md5_order[g * 32 + lane];
+                const bool active = c != 0xffffffffu;
+                const uint8_t *src = nullptr;
+                uint64_t len = 0;
+                if (active) {
+                    src = p.chunks[c].src;
+                    len = p.chunks[c].len;
+                }
+                volatile uint32_t *prog = p.md5_progress + g;
+                if (lane == 0) *prog = 1u;  // started, 0 rows consumed
+                md5_warp(reinterpret_cast<uint32_t *>(in + warp * kRingBytes), src, len, active, p.md5_out + (size_t)(active ? c : 0) * 16,
+                         lane, prog);
+                if (lane == 0) *prog = 0xffffffffu;
+                __syncwarp();
+            }
+        }
+        if (!do_lz4) return;
+        __syncthreads();  // the rings overlapped the block buffer
     }
     if (!do_lz4) return;
-    if (do_md5 && (p.flags & SKY_F_MD5_EXCLUSIVE)) {
-        // keep the sub-partition of an MD5 warp free: warps sharing (warp & 3) with an MD5-hosting
-        // warp of this CTA do no LZ4 work.
-        const unsigned sub = warp & 3;
-        if (sub * gridDim.x + blockIdx.x < p.n_groups) return;
-    }
+
     const bool pace = do_md5 && !(p.flags & SKY_F_NO_PACING);
-    const uint32_t total = p.rows * p.n_chunks;
-    uint8_t *scratch = p.scratch + ((size_t)blockIdx.x * kWarps + warp) * kScratchBytes;
-    for (;;) {
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(p.counters, 1u);
-        w = __shfl_sync(kFull, w, 0);
-        if (w >= total) break;
-        lz4_work(p, w % p.n_chunks, w / p.n_chunks, reinterpret_cast<uint32_t *>(my), scratch, lane, pace);
-        __syncwarp();
+    uint8_t *scratch = p.scratch + (size_t)blockIdx.x * kScratchBytes;
+    uint32_t gseq = 0;        // prober: sequence number of the next segment it publishes (runs across blocks)
+    uint32_t my_seq = 0;      // parser: the sequence number it holds a claim on
+    bool have_claim = false;
+    uint32_t in_phase = 0;
+    for (uint32_t it = 0;; it++) {
+        BlockDesc *dsc = &ctl->desc[it & 1];
+        if (threadIdx.x == 0) {
+            claim_block(p, dsc, pace);
+            ctl->block_end_seq = 0xffffffffu;
+            ctl->nseg = 0;
+        }
+        __syncthreads();  // (also: every warp is done with the previous block's buffer, records and plan)
+        if (!dsc->valid) break;
+        const uint8_t *src = dsc->src;
+        const uint32_t L = dsc->L;
+
+        if (warp == 0) {
+            // ---------------------------------------------------------------- prober
+            if (lane == 0) {
+                const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old block before the async write
+                mbar_arrive_expect_tx(&ctl->in_full, bytes);
+                bulk_load(in, src, bytes, &ctl->in_full);
+            }
+            {   // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty"
+                uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+                for (uint32_t k = lane; k < kEntries / 4; k += 32) t4[k] = z;
+            }
+            __syncwarp();
+            mbar_wait(&ctl->in_full, in_phase);
+            in_phase ^= 1;
+            uint32_t nseg = 0;
+            if (L >= kMfLimit + 1) {
+                const uint32_t mflimit = L - kMfLimit;
+                uint32_t seg_pos = 0, slog = 0;
+                while (seg_pos <= mflimit) {
+                    const uint32_t si = gseq % kRing, ph = (gseq / kRing) & 1u;
+                    mbar_wait(&ctl->empty[si], ph ^ 1u);
+                    SegSlot *slot = ring + si;
+                    const bool anyhit = probe_segment(smem_u32(in), smem_u32(tab), smem_u32(slot->offs), smem_u32(slot->masks), seg_pos, slog,
+                                                      mflimit, lane);
+                    if (kSegGroups < 32 && (int)lane >= kSegGroups) slot->masks[lane] = 0;
+                    if (lane == 0) {
+                        slot->seg_pos = seg_pos;
+                        slot->slog = slog;
+                        slot->sidx = nseg;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->full[si]);
+                    seg_pos += kSegSlots << slog;
+                    if (anyhit) slog = 0;
+                    else if (slog < kMaxStepLog) slog++;
+                    gseq++;
+                    nseg++;
+                }
+            }
+            if (lane == 0) {
+                ctl->nseg = nseg;
+                __threadfence_block();
+                ctl->block_end_seq = gseq;
+            }
+        } else {
+            // ---------------------------------------------------------------- parsers
+            mbar_wait(&ctl->in_full, in_phase);  // the block is in shared memory (the prober may still be clearing the table)
+            in_phase ^= 1;
+            for (;;) {
+                if (!have_claim) {
+                    uint32_t t = 0;
+                    if (lane == 0) t = atomicAdd(&ctl->claim, 1u);
+                    my_seq = __shfl_sync(kFull, t, 0);
+                    have_claim = true;
+                }
+                const uint32_t si = my_seq % kRing, ph = (my_seq / kRing) & 1u;
+                bool got = true;
+                while (!mbar_try_wait_hint(&ctl->full[si], ph, 1000u)) {
+                    if (ctl->block_end_seq <= my_seq) {  // this block has no such segment: keep the claim for the next block
+                        got = mbar_try_wait(&ctl->full[si], ph);
+                        break;
+                    }
+                }
+                if (!got) break;
+                const SegSlot *slot = ring + si;
+                const uint32_t sidx = slot->sidx;
+                uint8_t *scr = scratch + slot->seg_pos + sidx * kSegPad;
+                const SegRec r = parse_segment(in, slot, scr, L, lane);
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&ctl->empty[si]);
+                    recs[sidx] = r;
+                }
+                have_claim = false;
+            }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- plan (warp 0)
+        const uint32_t nseg = ctl->nseg;
+        if (warp == 0) {
+            uint32_t csize = 0;
+            if (lane == 0) {
+                uint32_t carry = 0, o = 0;
+                for (uint32_t s = 0; s < nseg; s++) {
+                    const SegRec r = recs[s];
+                    const uint32_t ml = r.lead_ml >> 16, t = r.off_t >> 16;
+                    SegPlan pl;
+                    pl.foff = o;
+                    pl.fll = 0;
+                    if (ml) {
+                        pl.fll = carry + (r.lead_ml & 0xffffu);
+                        o += seq_bytes_fast(pl.fll, ml);
+                        carry = t;
+                    } else {
+                        carry += t;
+                    }
+                    pl.moff = o;
+                    pl.pad = 0;
+                    o += r.mbytes;
+                    plans[s] = pl;
+                }
+                if (nseg == 0) carry = L;
+                ctl->last_lits = carry;
+                ctl->tail_off = o;  // where the final literal run starts (relative to the block's first data byte)
+                csize = o + 1 + carry + (carry >= 15 ? (carry - 15) / 255 + 1 : 0);
+            }
+            csize = __shfl_sync(kFull, csize, 0);
+            const bool raw = csize > L - 1;  // LZ4F_makeBlock: a block that does not shrink is stored
+            // OFF chain: learn where this block starts, tell the successor at once
+            uint64_t st = 0;
+            if (lane == 0) {
+                uint64_t *cw = p.chain + dsc->c;
+                unsigned ns = 128;
+                while (((st = ld_acquire(cw)) >> kOffBits) != dsc->j) {
+                    __nanosleep(ns);
+                    if (ns < 2048) ns <<= 1;
+                }
+                const uint64_t off = st & kOffMask;
+                const uint32_t bsize = raw ? L : csize;
+                const uint64_t end = off + 4 + bsize;
+                if (!dsc->last) st_release(p.chain + dsc->c, ((uint64_t)(dsc->j + 1) << kOffBits) | end);
+                uint8_t *hdr = dsc->dst + off;
+                const uint32_t hword = raw ? (L | 0x80000000u) : csize;
+                hdr[0] = (uint8_t)hword; hdr[1] = (uint8_t)(hword >> 8); hdr[2] = (uint8_t)(hword >> 16); hdr[3] = (uint8_t)(hword >> 24);
+                if (dsc->last) {
+                    uint8_t *e = dsc->dst + end;
+                    e[0] = e[1] = e[2] = e[3] = 0;  // EndMark
+                    p.out_len[dsc->c] = end + 4;
+                }
+                ctl->csize = csize;
+                ctl->raw = raw;
+                const uint64_t data = off + 4;
+                ctl->data_hi = (uint32_t)(data >> 32);
+                ctl->data_lo = (uint32_t)data;
+            }
+        }
+        __syncthreads();
+
+        // ---------------------------------------------------------------- write the block to its final place (all warps)
+        {
+            uint8_t *out = dsc->dst + (((uint64_t)ctl->data_hi << 32) | ctl->data_lo);
+            if (ctl->raw) {
+                // stored block: straight from the input (L2-hot: the bulk load just pulled it), 16-byte-aligned slices per warp
+                const uint32_t per = (((L + kWarps - 1) / kWarps) + 15u) & ~15u;
+                const uint32_t lo = warp * per;
+                if (lo < L) warp_copy_stream<true>(out + lo, src + lo, min(per, L - lo), lane);
+            } else {
+                for (uint32_t s = warp; s < nseg; s += kWarps) {
+                    const SegRec r = recs[s];
+                    const SegPlan pl = plans[s];
+                    const uint32_t ml = r.lead_ml >> 16;
+                    if (ml) {
+                        const uint32_t lit_start = r.seg_pos + (r.lead_ml & 0xffffu) - pl.fll;
+                        emit_seq(out, pl.foff, src, lit_start, pl.fll, ml, r.off_t & 0xffffu, lane);
+                    }
+                    if (r.mbytes) warp_copy_stream<false>(out + pl.moff, scratch + r.seg_pos + s * kSegPad, r.mbytes, lane);
+                }
+                if (warp == kWarps - 1) {
+                    const uint32_t ll = ctl->last_lits;
+                    emit_seq(out, ctl->tail_off, src, L - ll, ll, 0, 0, lane);
+                }
+            }
+        }
     }
 }
 
@@ -348,7 +552,7 @@ struct Slot {
     uint8_t *h_md5 = nullptr, *d_md5 = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_d2h = nullptr;  // input landed (on ctx->st_h2d) / frames landed (on ctx->st_d2h)
     uint32_t *d_counters = nullptr;
-    uint8_t *d_scratch = nullptr;  // compress scratch: kScratchBytes per warp of the grid (kernels of different slots overlap)
+    uint8_t *d_scratch = nullptr;  // compress scratch: kScratchBytes per CTA of the grid (kernels of different slots overlap)
     // receiver side
     DecChunk *h_dchunks = nullptr, *d_dchunks = nullptr;
     DecBlock *d_dblocks = nullptr;
@@ -441,7 +645,7 @@ uint32_t sky_kernel_config(int what) {
     switch (what) {
     case 0: return kEntries;
     case 1: return (uint32_t)kWarps;
-    case 2: return kTile;
+    case 2: return kSegSlots;
     case 3: return kMaxStepLog;
     default: return 0;
     }
@@ -469,7 +673,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
     CK(ctx, cudaMalloc(&s.d_counters, 64));
-    CK(ctx, cudaMalloc(&s.d_scratch, (size_t)ctx->sm_count * kWarps * kScratchBytes));
+    CK(ctx, cudaMalloc(&s.d_scratch, (size_t)ctx->sm_count * kCtasPerSm * kScratchBytes));
     CK(ctx, cudaMallocHost(&s.h_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMalloc(&s.d_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMallocHost(&s.h_dstatus, nc * sizeof(int32_t)));
@@ -530,6 +734,7 @@ int sky_ctx_create(int device, uint64_t max_batch_bytes, uint32_t max_chunks, ui
     if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return fail(SKY_E_CUDA); }
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaFuncSetAttribute(sky_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sky_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (e != cudaSuccess) {
         ctx->err = std::string("cudaFuncSetAttribute(smem): ") + cudaGetErrorString(e) + " (built for sm_100a only)";
         return fail(SKY_E_CUDA);
@@ -593,10 +798,6 @@ int sky_pinned_free(void *p) {
 static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t meta_st, uint32_t n, const uint8_t *d_src,
                         const uint64_t *src_off, const uint64_t *src_len, uint8_t *d_dst, const uint64_t *dst_off, uint32_t flags) {
     if ((flags & (SKY_F_LZ4 | SKY_F_MD5)) == 0) flags |= SKY_F_LZ4 | SKY_F_MD5;
-    // Few long chunks: the MD5 chains are the critical path, so the sub-partition hosting an MD5 warp is kept free
-    // of LZ4 warps (measured: Silesia-like 256 x 8 MiB, 86 ms shared vs 74 ms exclusive vs 70.7 ms MD5 alone).  With
-    // more groups than SMs the LZ4 capacity lost would outweigh it.
-    if ((n + 31) / 32 <= (uint32_t)ctx->sm_count) flags |= SKY_F_MD5_EXCLUSIVE;
     uint32_t rows = 1;
     for (uint32_t i = 0; i < n; i++) {
         ChunkDesc &d = s.h_desc[i];
@@ -641,10 +842,13 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     p.scratch = s.d_scratch;
     p.n_chunks = n;
     p.n_groups = ng;
+    const uint32_t grid = (uint32_t)ctx->sm_count * kCtasPerSm;
+    // digest CTAs: 4 groups (one per SM sub-partition) each; with few groups spread them one per CTA first
+    p.n_md5_ctas = (flags & SKY_F_MD5) ? std::min(grid, std::max((ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta, std::min(ng, (uint32_t)ctx->sm_count / 4))) : 0;
     p.rows = rows;
     p.flags = flags;
     CK(ctx, cudaEventRecord(s.ev_k0, st));
-    sky_fused_kernel<<<ctx->sm_count, kThreads, kSmemBytes, st>>>(p);
+    sky_fused_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaEventRecord(s.ev_k1, st));
     ctx->launches++;

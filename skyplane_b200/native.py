@@ -125,7 +125,7 @@ def device_pci_bus_id(device: int) -> str:
 def kernel_config() -> dict:
     """Compile-time constants of the loaded build (sky_kernel_config)."""
     L = lib()
-    return {"lz4_entries": L.sky_kernel_config(0), "warps": L.sky_kernel_config(1), "tile": L.sky_kernel_config(2),
+    return {"lz4_entries": L.sky_kernel_config(0), "warps": L.sky_kernel_config(1), "seg_slots": L.sky_kernel_config(2),
             "max_step_log": L.sky_kernel_config(3)}
 
 

@@ -14,7 +14,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from tools import tile_model as tm  # noqa: E402
 
 
-@pytest.mark.parametrize("opts", [tm.kernel_opts(), tm.kernel_opts(3072), tm.kernel_opts(2048, 256, 0), tm.Opts(4096, 8, 1024, 8, 1, 2, 1, 1)])
+@pytest.mark.parametrize("opts", [tm.kernel_opts(), tm.kernel_opts(3072, 512), tm.kernel_opts(2048, 256, 0), tm.Opts(4096, 1024, 4, 0, 0)])
 def test_model_emits_valid_lz4(opts):
     rng = np.random.default_rng(3)
     datas = [rng.bytes(n) for n in (1, 12, 13, 100, 65536)] + [bytes(70000), (b"abcdefg" * 20000)[:131073], b"",
@@ -28,8 +28,8 @@ def test_model_emits_valid_lz4(opts):
 
 
 def test_kernel_parse_ratio_close_to_reference():
-    """The shipped parse (4096 entries, 5-byte hash, backward extension) keeps >= 0.96 x the reference's ratio."""
+    """The shipped parse (4096 entries, 5-byte hash, backward extension) keeps >= 0.965 x the reference's ratio."""
     datas = [synth.silesia_like_chunk(i, 4 << 20) for i in range(2)]
     ours = sum(len(tm.frame(d)) for d in datas)
     refsz = sum(len(ref.lz4f_compress(d)) for d in datas)
-    assert refsz / ours >= 0.96
+    assert refsz / ours >= 0.965

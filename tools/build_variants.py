@@ -8,11 +8,10 @@ sys.path.insert(0, str(ROOT))
 from skyplane_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "e4096_w13": {"SKY_LZ4_ENTRIES": 4096, "SKY_WARPS": 13},
-    "e4096_w12": {"SKY_LZ4_ENTRIES": 4096, "SKY_WARPS": 12},
-    "e3072_w18": {"SKY_LZ4_ENTRIES": 3072, "SKY_WARPS": 18},
-    "e2048_w26": {"SKY_LZ4_ENTRIES": 2048, "SKY_WARPS": 26},
-    "e2048_w16": {"SKY_LZ4_ENTRIES": 2048, "SKY_WARPS": 16},
+    "p10_e4096": {"SKY_PARSERS": 10, "SKY_LZ4_ENTRIES": 4096},
+    "p8_e4096": {"SKY_PARSERS": 8, "SKY_LZ4_ENTRIES": 4096},
+    "p6_e4096": {"SKY_PARSERS": 6, "SKY_LZ4_ENTRIES": 4096},
+    "p12_e3072": {"SKY_PARSERS": 12, "SKY_LZ4_ENTRIES": 3072},
 }
 
 if __name__ == "__main__":

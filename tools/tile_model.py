@@ -13,17 +13,17 @@ _lib = None
 
 
 class Opts(ctypes.Structure):
-    _fields_ = [("entries", ctypes.c_int), ("tag_bits", ctypes.c_int), ("tile", ctypes.c_int), ("max_step", ctypes.c_int),
-                ("back_ext", ctypes.c_int), ("ways", ctypes.c_int), ("policy", ctypes.c_int), ("hash5", ctypes.c_int)]
+    _fields_ = [("entries", ctypes.c_int), ("seg_slots", ctypes.c_int), ("max_step_log", ctypes.c_int), ("back_ext", ctypes.c_int),
+                ("clip", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint64) for n in ("probes", "hits", "verified", "accepted", "tiles")]
+    _fields_ = [(n, ctypes.c_uint64) for n in ("probes", "hits", "accepted", "segments")]
 
 
-def kernel_opts(entries: int = 4096, tile: int = 256, max_step_log: int = 4) -> Opts:
+def kernel_opts(entries: int = 4096, seg_slots: int = 1024, max_step_log: int = 4) -> Opts:
     """The options the kernel in skyplane_b200/csrc/lz4.cuh implements."""
-    return Opts(entries, 16, tile, 1 << max_step_log, 2, 1, 0, 2)
+    return Opts(entries, seg_slots, max_step_log, 1, 1)
 
 
 def lib():
@@ -59,7 +59,7 @@ def _xxh32_small(b: bytes) -> int:  # XXH32, seed 0, inputs < 16 bytes (the fram
 def blocks(data: bytes, o: Opts):
     """-> list of (compressed size or 0 when stored raw, block bytes as they appear in the frame)."""
     L = lib()
-    buf = ctypes.create_string_buffer(65536 + 1024)
+    buf = ctypes.create_string_buffer(65536 + 4096)
     out = []
     for pos in range(0, len(data), 65536):
         blk = data[pos:pos + 65536]

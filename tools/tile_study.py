@@ -4,7 +4,6 @@ Prints frame-size ratios for design variants next to liblz4's (linked blocks = w
 Every model output is decoded with liblz4 to prove the variant emits valid LZ4."""
 import ctypes
 import json
-import subprocess
 import sys
 from pathlib import Path
 
@@ -14,38 +13,24 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from skyplane_b200 import synth  # noqa: E402
 
-SO = ROOT / "tools" / "bin" / "liblz4tile.so"
-SO.parent.mkdir(exist_ok=True)
-subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(SO), str(ROOT / "tools" / "lz4_tile_model.c")])
-M = ctypes.CDLL(str(SO))
+from tools import tile_model as tm  # noqa: E402
+
+M = tm.lib()
+Opts, Stats = tm.Opts, tm.Stats
 LZ4 = ctypes.CDLL("liblz4.so.1")
-
-
-class Opts(ctypes.Structure):
-    _fields_ = [("entries", ctypes.c_int), ("tag_bits", ctypes.c_int), ("tile", ctypes.c_int), ("max_step", ctypes.c_int),
-                ("back_ext", ctypes.c_int), ("ways", ctypes.c_int), ("policy", ctypes.c_int), ("hash5", ctypes.c_int)]
-
-
-class Stats(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint64) for n in ("probes", "hits", "verified", "accepted", "tiles")]
-
-
-M.tile_compress_block.argtypes = [ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.POINTER(Opts)]
-M.tile_compress_block.restype = ctypes.c_uint32
 LZ4.LZ4_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
 
 
 def model_size(data: bytes, o: Opts, check: bool = True) -> int:
-    total = 15 + 4
-    out = ctypes.create_string_buffer(65536 + 16)
+    total, pos = 15 + 4, 0
     back = ctypes.create_string_buffer(65536)
-    for pos in range(0, len(data), 65536):
-        blk = data[pos: pos + 65536]
-        c = M.tile_compress_block(blk, len(blk), out, ctypes.byref(o))
+    for c, b in tm.blocks(data, o):
+        n = min(65536, len(data) - pos)
         if c and check:
-            r = LZ4.LZ4_decompress_safe(out, back, c, len(blk))
-            assert r == len(blk) and back.raw[:r] == blk, "model emitted an invalid block"
-        total += 4 + (c or len(blk))
+            r = LZ4.LZ4_decompress_safe(b, back, c, 65536)
+            assert r == n and back.raw[:r] == data[pos:pos + n], "model emitted an invalid block"
+        pos += n
+        total += 4 + len(b)
     return total
 
 
@@ -56,10 +41,14 @@ def liblz4_linked_size(data: bytes) -> int:
 
 
 VARIANTS = {
-    "h5m p0 back2 4096e T256 step16": Opts(4096, 16, 256, 16, 2, 1, 0, 2),
-    "h5m p0 back2 3072e T256 step16": Opts(3072, 16, 256, 16, 2, 1, 0, 2),
-    "h5m p0 back2 2048e T256 step16": Opts(2048, 16, 256, 16, 2, 1, 0, 2),
-    "h5m p0 back2 4096e T256 step1": Opts(4096, 16, 256, 1, 2, 1, 0, 2),
+    "kernel: 4096e seg1024 step16": tm.kernel_opts(),
+    "no segment clipping": Opts(4096, 1024, 4, 1, 0),
+    "seg512": tm.kernel_opts(4096, 512),
+    "seg2048": tm.kernel_opts(4096, 2048),
+    "3072e": tm.kernel_opts(3072),
+    "2048e": tm.kernel_opts(2048),
+    "no back ext": Opts(4096, 1024, 4, 0, 1),
+    "step1": tm.kernel_opts(4096, 1024, 0),
 }
 
 if __name__ == "__main__":
@@ -77,7 +66,6 @@ if __name__ == "__main__":
             M.tile_model_stats(ctypes.byref(st), 1)
             row[vname] = round(raw / sum(model_size(d, o) for d in datas), 4)
             M.tile_model_stats(ctypes.byref(st), 1)
-            if vname.startswith("h5m p0 back2 4096e T256 step16"):
-                row["stats"] = {"probes/B": round(st.probes / raw, 3), "hits/B": round(st.hits / raw, 3),
-                                "verified/B": round(st.verified / raw, 4), "B/seq": round(raw / max(1, st.accepted), 1)}
+            if vname.startswith("kernel:"):
+                row["stats"] = {"probes/B": round(st.probes / raw, 3), "hits/B": round(st.hits / raw, 3), "B/seq": round(raw / max(1, st.accepted), 1)}
         print(json.dumps(row), flush=True)
