@@ -247,9 +247,7 @@ __device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const ui
 #ifndef SKY_MAX_STEP_LOG
 #define SKY_MAX_STEP_LOG 4
 #endif
-#ifndef SKY_SEG_GROUPS
-#define SKY_SEG_GROUPS 32
-#endif
+#define SKY_SEG_GROUPS 32   // (fixed: 4 prober batches of 8 groups; a parser lane holds one group's hit mask)
 constexpr uint32_t kCoopLit = SKY_COOP_LIT;          // literal runs at least this long are copied by the whole warp
 constexpr uint32_t kMaxStepLog = SKY_MAX_STEP_LOG;   // probe stride doubles after a segment without a hit, up to 1 << this
 constexpr int kSegGroups = SKY_SEG_GROUPS;           // a segment = this many warp-wide groups of probe slots (<= 32)
@@ -429,11 +427,15 @@ __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t 
     return op + total;
 }
 
-// ---- prober: one segment.  Writes the segment's hit masks and candidate offsets; returns whether any slot hit.
-// Software-pipelined 8 groups at a time: everything that does not depend on the table (input words, hash, the match.any
-// ordering of the lanes, the in-group candidate) is computed for all 8 groups first; then the 8 table lookups and stores
-// are issued back to back (the LSU keeps a warp's shared-memory accesses in order, so group k+1's lookup sees group k's
-// store without waiting for group k's lookup to return); only then are the lookups' results consumed.
+// ---- prober: one batch of 8 groups (256 probe slots) of a segment.
+// Phase A -- everything that does not depend on the table: input words, hash, the match.any ordering of the lanes (which
+// lane is the most recent earlier occurrence inside the group, which lane stores) -- for all 8 groups.  match.any takes time
+// in proportion to the number of distinct values (32 rounds when all lanes differ, the common case), so the CTA runs TWO
+// prober warps that take alternate batches: one warp's phase A overlaps the other's table phase.
+// `turn()` is called between the phases: it returns when the other prober has finished the previous batch's table phase.
+// Phase B -- the 8 table lookups and stores back to back (the LSU keeps a warp's shared-memory accesses in order, so group
+// k+1's lookup sees group k's store without waiting for group k's lookup to return).  Phase C -- consume the lookups:
+// hit masks and candidate offsets into the segment's ring slot.  Returns the OR of the batch's hit masks.
 // Slots past the last probe position (p > mflimit, only at the very end of a block, always the highest lanes) hash a
 // clamped position and are masked out of the hits; they may win a table store, which no later lookup can observe.
 __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (0xffffffff for 0): one FLO
@@ -441,57 +443,55 @@ __device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest
     asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
     return r;
 }
-__device__ __forceinline__ bool probe_segment(uint32_t in_s, uint32_t tab_s, uint32_t offs_s, uint32_t masks_s, uint32_t seg_pos,
-                                              uint32_t slog, uint32_t mflimit, unsigned lane) {
+template <class Turn>
+__device__ __forceinline__ uint32_t probe_batch(uint32_t in_s, uint32_t tab_s, uint32_t offs_s, uint32_t masks_s, uint32_t seg_pos,
+                                                uint32_t slog, uint32_t batch, uint32_t mflimit, unsigned lane, Turn turn) {
     const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~((2u << lane) - 1u);
     const uint32_t pstep = 32u << slog;
-    uint32_t p = seg_pos + (lane << slog);
+    uint32_t p = seg_pos + ((batch * 256u + lane) << slog);
     // p & 3 is the same for every group of the segment (p advances by a multiple of 32): byte selectors are loop-invariant
     const uint32_t selv = 0x3210u + 0x1111u * (p & 3u), selb = 0x4440u | (p & 3u);
-    uint32_t offs_l = offs_s + lane * 2u, anyhit = 0;
-#pragma unroll 1
-    for (int g0 = 0; g0 < kSegGroups; g0 += 8) {
-        uint32_t idx[8], mine[8], e[8], e_near[8];
-        bool valid[8], has_lower[8], stores[8];
+    const uint32_t offs_l = offs_s + (batch * 256u + lane) * 2u;
+    uint32_t idx[8], mine[8], e[8], e_near[8], anyhit = 0;
+    bool valid[8], has_lower[8], stores[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            valid[k] = p <= mflimit;
-            const uint32_t pc = min(p, mflimit);
-            const uint32_t a = in_s + (pc & ~3u);
-            const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
-            uint32_t hf = __byte_perm(w0, w1, selv) * 2654435761u;
-            hf = __byte_perm(w1, 0u, selb) * 0x85EBCA6Bu + hf;  // fifth byte
-            idx[k] = __umulhi(hf, kEntries) * 4u;               // byte offset of the table entry
-            mine[k] = __byte_perm(p, hf, 0x6510);               // pos16 | hash bytes 1-2 as the tag
-            p += pstep;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const unsigned grp = __match_any_sync(kFull, idx[k]);
-            const unsigned lower = grp & lt_mask;
-            has_lower[k] = lower != 0u;
-            e_near[k] = __shfl_sync(kFull, mine[k], bfind(lower));  // nearest lower lane = most recent occurrence (unused if none)
-            stores[k] = (grp & gt_mask) == 0u;                      // the highest lane of the group stores
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            e[k] = lds32(tab_s + idx[k]);
-            __syncwarp();  // (orders the lanes' table reads of this group before its writes)
-            if (stores[k]) sts32(tab_s + idx[k], mine[k]);
-            __syncwarp();
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const uint32_t ek = has_lower[k] ? e_near[k] : e[k];  // a lower lane filled the slot more recently than the table knows
-            const uint32_t x = ek ^ mine[k];
-            const unsigned hits = __ballot_sync(kFull, valid[k] && (x - 1u) < 65535u);  // tag equal, position differs
-            anyhit |= hits;
-            if (lane == 0) sts32(masks_s + (uint32_t)(g0 + k) * 4u, hits);
-            sts16(offs_l + (uint32_t)k * 64u, mine[k] - ek);
-        }
-        offs_l += 8u * 64u;
+    for (int k = 0; k < 8; k++) {
+        valid[k] = p <= mflimit;
+        const uint32_t pc = min(p, mflimit);
+        const uint32_t a = in_s + (pc & ~3u);
+        const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
+        uint32_t hf = __byte_perm(w0, w1, selv) * 2654435761u;
+        hf = __byte_perm(w1, 0u, selb) * 0x85EBCA6Bu + hf;  // fifth byte
+        idx[k] = __umulhi(hf, kEntries) * 4u;               // byte offset of the table entry
+        mine[k] = __byte_perm(p, hf, 0x6510);               // pos16 | hash bytes 1-2 as the tag
+        p += pstep;
     }
-    return anyhit != 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned grp = __match_any_sync(kFull, idx[k]);
+        const unsigned lower = grp & lt_mask;
+        has_lower[k] = lower != 0u;
+        e_near[k] = __shfl_sync(kFull, mine[k], bfind(lower));  // nearest lower lane = most recent occurrence (unused if none)
+        stores[k] = (grp & gt_mask) == 0u;                      // the highest lane of the group stores
+    }
+    turn();
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        e[k] = lds32(tab_s + idx[k]);
+        __syncwarp();  // (orders the lanes' table reads of this group before its writes)
+        if (stores[k]) sts32(tab_s + idx[k], mine[k]);
+        __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t ek = has_lower[k] ? e_near[k] : e[k];  // a lower lane filled the slot more recently than the table knows
+        const uint32_t x = ek ^ mine[k];
+        const unsigned hits = __ballot_sync(kFull, valid[k] && (x - 1u) < 65535u);  // tag equal, position differs
+        anyhit |= hits;
+        if (lane == 0) sts32(masks_s + (batch * 8u + (uint32_t)k) * 4u, hits);
+        sts16(offs_l + (uint32_t)k * 64u, mine[k] - ek);
+    }
+    return anyhit;
 }
 
 // ---- parser: one segment.  in = shared-memory copy of the block, scr = this segment's scratch area.

@@ -44,10 +44,11 @@
 namespace sky {
 
 #ifndef SKY_PARSERS
-#define SKY_PARSERS 10
+#define SKY_PARSERS 9
 #endif
 constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
-constexpr int kWarps = 1 + kParsers;      // + the prober (warp 0)
+constexpr int kProbers = 2;               // prober warps (0 and 1): they take alternate 256-slot batches
+constexpr int kWarps = kProbers + kParsers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRing = kParsers + 3;       // segment slots between the prober and the parsers
 constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
@@ -70,6 +71,7 @@ struct Ctl {
     uint32_t claim;                 // next segment sequence number a parser may take (runs across blocks)
     volatile uint32_t block_end_seq;  // sequence number after the current block's last segment (0xffffffff while probing)
     volatile uint32_t nseg;
+    volatile uint32_t seg_hit[4];     // per segment (mod 4): OR of its batches' hit masks (decides the stride two segments on)
     uint32_t csize, raw, last_lits, tail_off;   // plan results: compressed size, stored?, final literal run and where it goes
     uint32_t data_lo, data_hi;                  // frame offset of the block's first data byte
 };
@@ -126,6 +128,11 @@ __device__ __forceinline__ void st_release(uint64_t *p, uint64_t v) {
 __device__ __forceinline__ void st_release32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// named-barrier token between the two prober warps: the releaser arrives, the waiter syncs (ids 1 and 2, 64 threads)
+template <int kId>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, 64;" ::"n"(kId) : "memory"); }
+template <int kId>
+__device__ __forceinline__ void bar_wait() { asm volatile("bar.sync %0, 64;" ::"n"(kId) : "memory"); }
 __device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -238,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
 
     const bool pace = do_md5 && !(p.flags & SKY_F_NO_PACING);
     uint8_t *scratch = p.scratch + (size_t)blockIdx.x * kScratchBytes;
-    uint32_t gseq = 0;        // prober: sequence number of the next segment it publishes (runs across blocks)
+    uint32_t gseq = 0;        // probers: sequence number of the next segment they publish (runs across blocks)
+    uint32_t batches_done = 0;  // prober 0: nothing to wait for before the kernel's very first batch
     uint32_t my_seq = 0;      // parser: the sequence number it holds a claim on
     bool have_claim = false;
     uint32_t in_phase = 0;
@@ -254,21 +262,23 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
         const uint8_t *src = dsc->src;
         const uint32_t L = dsc->L;
 
-        if (warp == 0) {
-            // ---------------------------------------------------------------- prober
-            if (lane == 0) {
-                const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old block before the async write
-                mbar_arrive_expect_tx(&ctl->in_full, bytes);
-                bulk_load(in, src, bytes, &ctl->in_full);
-            }
-            {   // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty"
+        if (warp < kProbers) {
+            // ---------------------------------------------------------------- probers (warps 0 and 1, alternate batches)
+            if (warp == 0) {
+                if (lane == 0) {
+                    const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old block before the async write
+                    mbar_arrive_expect_tx(&ctl->in_full, bytes);
+                    bulk_load(in, src, bytes, &ctl->in_full);
+                }
+                // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty".  (Warp 1's first table access
+                // follows warp 0's first table phase through the token, so it sees the cleared table.)
                 uint4 *t4 = reinterpret_cast<uint4 *>(tab);
                 const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
                 for (uint32_t k = lane; k < kEntries / 4; k += 32) t4[k] = z;
+                __syncwarp();
             }
-            __syncwarp();
             mbar_wait(&ctl->in_full, in_phase);
             in_phase ^= 1;
             uint32_t nseg = 0;
@@ -276,27 +286,44 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 const uint32_t mflimit = L - kMfLimit;
                 uint32_t seg_pos = 0, slog = 0;
                 while (seg_pos <= mflimit) {
-                    const uint32_t si = gseq % kRing, ph = (gseq / kRing) & 1u;
-                    mbar_wait(&ctl->empty[si], ph ^ 1u);
-                    SegSlot *slot = ring + si;
-                    const bool anyhit = probe_segment(smem_u32(in), smem_u32(tab), smem_u32(slot->offs), smem_u32(slot->masks), seg_pos, slog,
-                                                      mflimit, lane);
-                    if (kSegGroups < 32 && (int)lane >= kSegGroups) slot->masks[lane] = 0;
-                    if (lane == 0) {
-                        slot->seg_pos = seg_pos;
-                        slot->slog = slog;
-                        slot->sidx = nseg;
+                    if (nseg >= 2) {  // the verdict on segment nseg-2 decides this segment's stride
+                        const bool h = ctl->seg_hit[(nseg - 2) & 3u] != 0u;
+                        slog = h ? 0u : min(slog + 1u, kMaxStepLog);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->full[si]);
+                    const uint32_t si = gseq % kRing, ph = (gseq / kRing) & 1u;
+                    SegSlot *slot = ring + si;
+#pragma unroll 1
+                    for (uint32_t b = warp; b < 4; b += kProbers) {
+                        const uint32_t hits = probe_batch(smem_u32(in), smem_u32(tab), smem_u32(slot->offs), smem_u32(slot->masks), seg_pos, slog, b,
+                                                          mflimit, lane, [&]() {
+                            // my turn at the table: the other prober has finished the previous batch
+                            if (warp == 0) {
+                                if (batches_done) bar_wait<2>();
+                                if (b == 0) mbar_wait(&ctl->empty[si], ph ^ 1u);  // the ring slot is free again
+                            } else {
+                                bar_wait<1>();
+                            }
+                        });
+                        batches_done = 1;
+                        if (lane == 0) {
+                            ctl->seg_hit[nseg & 3u] = (b == 0 ? 0u : ctl->seg_hit[nseg & 3u]) | hits;
+                            if (b == 0) {
+                                slot->seg_pos = seg_pos;
+                                slot->slog = slog;
+                                slot->sidx = nseg;
+                            }
+                        }
+                        __syncwarp();
+                        if (b == 3 && lane == 0) mbar_arrive(&ctl->full[si]);  // (release: both probers' slot writes are ordered before it)
+                        __threadfence_block();
+                        if (warp == 0) bar_arrive<1>(); else bar_arrive<2>();  // pass the token
+                    }
                     seg_pos += kSegSlots << slog;
-                    if (anyhit) slog = 0;
-                    else if (slog < kMaxStepLog) slog++;
                     gseq++;
                     nseg++;
                 }
             }
-            if (lane == 0) {
+            if (warp == kProbers - 1 && lane == 0) {
                 ctl->nseg = nseg;
                 __threadfence_block();
                 ctl->block_end_seq = gseq;

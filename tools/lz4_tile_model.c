@@ -8,7 +8,9 @@
  *
  * The parse, per 64 KiB block (the kernel runs it with one CTA per block: a prober warp and several parser warps):
  *   segment = seg_slots probe slots, slot i at position seg_pos + (i << slog); segments tile the block back to back.
- *             slog is 0, and grows by one (up to max_step_log) after a segment without any hit; any hit resets it.
+ *             slog starts at 0 for the first two segments; segment s+2's slog is 0 if segment s had any hit, else segment
+ *             s+1's slog plus one (up to max_step_log) -- one segment of delay, so the kernel's two prober warps never
+ *             wait for each other's verdict.
  *   probe   = every slot, in position order: hash 5 bytes, look the table entry (pos16 | tag16) up; hit = tag equal and
  *             entry older than the slot; the slot then replaces the entry.  No byte of the candidate is read here.
  *   parse   = per segment, independently of every other segment: cursor and anchor start at the segment start; walk the
@@ -64,7 +66,7 @@ uint32_t tile_compress_block(const uint8_t *src, uint32_t L, uint8_t *out, const
     uint32_t anchor = 0 /* start of the literals not yet emitted */, op = 0, result = 0;
     if (L >= MFLIMIT + 1) {
         const uint32_t mflimit = L - MFLIMIT, matchlimit = L - LASTLITERALS;
-        uint32_t seg_pos = 0, slog = 0;
+        uint32_t seg_pos = 0, slog = 0, slog_next = 0;  /* slog of this segment / of the next one */
         while (seg_pos <= mflimit) {
             g_stats.segments++;
             /* ---- probe (sequential insertion; the kernel reproduces it 32 slots at a time with match.any) */
@@ -109,8 +111,11 @@ uint32_t tile_compress_block(const uint8_t *src, uint32_t L, uint8_t *out, const
                 if (op > L + 1024) goto done;  /* (model only) hopeless and about to overrun the caller's buffer */
             }
             seg_pos = seg_lim;
-            if (anyhit) slog = 0;
-            else if (slog < (uint32_t)o->max_step_log) slog++;
+            {   /* this segment's verdict decides the stride two segments on */
+                const uint32_t after = anyhit ? 0 : (slog_next < (uint32_t)o->max_step_log ? slog_next + 1 : slog_next);
+                slog = slog_next;
+                slog_next = after;
+            }
         }
     }
     if (L - anchor + (L - anchor) / 255 + 2 + op <= L + 2040) op = emit(out, op, src, anchor, L - anchor, 0, 0);
