@@ -366,10 +366,12 @@ __device__ __forceinline__ uint32_t extend_coop_s(uint32_t in32, uint32_t mpos, 
 // q0 = literal length | match length << 16, q1 = literal start | offset << 16 (lane k = k-th sequence).  Literals come
 // from the shared-memory copy of the block, output goes to the segment's scratch area.  Sizes go through a warp scan; every
 // lane writes its own token, length bytes, literals (runs >= kCoopLit: one warp copy each), offset and match-length bytes.
+// skip_first: lane 0 holds the segment's FIRST sequence, which is not emitted here (its literal run is completed with the
+// literals carried over from earlier segments when the block is assembled).
 __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t op, const uint8_t *in, uint32_t q0, uint32_t q1,
-                                            uint32_t nseq, unsigned lane) {
+                                            uint32_t nseq, bool skip_first, unsigned lane) {
     const uint32_t in32 = smem_u32(in);
-    const bool act = lane < nseq;
+    const bool act = lane < nseq && !(skip_first && lane == 0);
     const uint32_t ll = q0 & 0xffffu, ml = q0 >> 16, lit = q1 & 0xffffu, off = q1 >> 16;
     const uint32_t mcode = ml - kMinMatch;
     const uint32_t nl = ll >= 15 ? div255(ll - 15) + 1 : 0, nm = mcode >= 15 ? div255(mcode - 15) + 1 : 0;
@@ -495,6 +497,7 @@ __device__ __forceinline__ uint32_t probe_batch(uint32_t in_s, uint32_t tab_s, u
 }
 
 // ---- parser: one segment.  in = shared-memory copy of the block, scr = this segment's scratch area.
+// (Hits only exist at positions <= L-12 inside the segment, so a hit position is always below the match limit.)
 __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot *slot, uint8_t *__restrict__ scr, uint32_t L,
                                                 unsigned lane) {
     const uint32_t in32 = smem_u32(in), offs_s = smem_u32(slot->offs);
@@ -505,11 +508,12 @@ __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot
     const uint32_t mlim = min(matchlimit, seg_lim);                 // matches end at or before this
     const uint32_t seg_end = seg_lim > mflimit ? L : seg_lim;      // the last segment owns the block's tail
     const uint32_t round_up = (1u << slog) - 1u;
-    const int dl = lane < 23 ? (int)lane : (int)lane - 32;  // byte this lane compares: +0..+22 ahead, -1..-8 behind (lane 31 = -1)
+    const uint32_t dl = lane < 23 ? lane : lane - 32u;      // byte this lane compares: +0..+22 ahead, -1..-8 behind (lane 31 = -1)
     const uint32_t jrel = lane < 23 ? lane : 31u - lane;    // its distance from the match start
+    const bool fwd_lane = lane < 23;
     uint32_t anchor = seg_pos, cur = seg_pos, nseq = 0, q0 = 0, q1 = 0, mbytes = 0;
-    uint32_t first_lead_ml = 0, first_off = 0;
-    bool first = true;
+    uint32_t first_q0 = 0, first_q1 = 0;
+    bool first_pending = true;  // the segment's first sequence sits in lane 0 of the first batch
     unsigned nz = __ballot_sync(kFull, mymask != 0u);
     uint32_t m = 0, gbase = 0, sbase = 0;
     for (;;) {
@@ -525,47 +529,53 @@ __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot
         }
         const uint32_t bit = (uint32_t)__ffs(m) - 1u;
         uint32_t pos = gbase + (bit << slog);
-        if (pos >= mlim) break;  // nothing from here on can hold a match
         const uint32_t off = lds16(offs_s + (sbase + bit) * 2u);
         const uint32_t cand = pos - off;
         const uint32_t maxlen = mlim - pos;
         const uint32_t room = min(min(pos - anchor, cand), 8u);
         bool ok = false;
-        if (jrel < (lane < 23 ? maxlen : room)) ok = lds8(in32 + pos + (uint32_t)dl) == lds8(in32 + cand + (uint32_t)dl);
+        if (jrel < (fwd_lane ? maxlen : room)) ok = lds8(in32 + pos + dl) == lds8(in32 + cand + dl);
         const unsigned z = ~__ballot_sync(kFull, ok) | 0x00800000u;  // bit 23 = stop bit of the forward scan
         uint32_t mlen = (uint32_t)__ffs(z) - 1u;                   // 0..23
-        if (mlen == 23u && maxlen > 23u) mlen = extend_coop_s(in32, pos, cand, 23u, maxlen, lane);
-        if (mlen < kMinMatch) {  // tag collision
-            m &= m - 1;
-            continue;
+        if (mlen - kMinMatch >= 23u - kMinMatch) {  // rare: a tag collision (< 4), or the match runs past the 23 bytes compared
+            if (mlen < kMinMatch) {
+                m &= m - 1;
+                continue;
+            }
+            if (maxlen > 23u) mlen = extend_coop_s(in32, pos, cand, 23u, maxlen, lane);
         }
         const uint32_t back = (uint32_t)__clz(z);  // 0..8 (lane 31 = byte -1)
         const uint32_t end = pos + mlen;
         pos -= back;
         mlen += back;
-        if (first) {
-            first = false;
-            first_lead_ml = (pos - seg_pos) | (mlen << 16);
-            first_off = off;
-        } else {
-            const uint32_t r0 = (pos - anchor) | (mlen << 16), r1 = anchor | (off << 16);
-            if (lane == nseq) {
-                q0 = r0;
-                q1 = r1;
-            }
-            if (++nseq == 32) {
-                mbytes = flush_seqs(scr, mbytes, in, q0, q1, 32, lane);
-                nseq = 0;
-            }
+        const uint32_t r0 = (pos - anchor) | (mlen << 16), r1 = anchor | (off << 16);
+        if (lane == nseq) {
+            q0 = r0;
+            q1 = r1;
         }
         anchor = cur = end;
         m &= __funnelshift_lc(0u, 0xffffffffu, (cur - gbase + round_up) >> slog);
+        if (++nseq == 32) {
+            if (first_pending) {
+                first_q0 = __shfl_sync(kFull, q0, 0);
+                first_q1 = __shfl_sync(kFull, q1, 0);
+            }
+            mbytes = flush_seqs(scr, mbytes, in, q0, q1, 32, first_pending, lane);
+            first_pending = false;
+            nseq = 0;
+        }
     }
-    if (nseq) mbytes = flush_seqs(scr, mbytes, in, q0, q1, nseq, lane);
+    if (nseq) {
+        if (first_pending) {
+            first_q0 = __shfl_sync(kFull, q0, 0);
+            first_q1 = __shfl_sync(kFull, q1, 0);
+        }
+        mbytes = flush_seqs(scr, mbytes, in, q0, q1, nseq, first_pending, lane);
+    }
     SegRec r;
     r.seg_pos = seg_pos;
-    r.lead_ml = first_lead_ml;
-    r.off_t = first_off | ((seg_end - anchor) << 16);
+    r.lead_ml = first_q0;                                            // lead literals | match length << 16 (0: no match)
+    r.off_t = (first_q1 >> 16) | ((seg_end - anchor) << 16);        // offset | trailing literals << 16
     r.mbytes = mbytes;
     return r;
 }

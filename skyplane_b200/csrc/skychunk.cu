@@ -44,7 +44,7 @@
 namespace sky {
 
 #ifndef SKY_PARSERS
-#define SKY_PARSERS 9
+#define SKY_PARSERS 10
 #endif
 constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
 constexpr int kProbers = 2;               // prober warps (0 and 1): they take alternate 256-slot batches
