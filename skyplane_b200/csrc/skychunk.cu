@@ -53,6 +53,7 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kRing = kParsers + 3;       // segment slots between the prober and the parsers
 constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
+constexpr uint32_t kLoadPiece = 8192;     // bytes per bulk copy of the block load
 constexpr int kCtasPerSm = 2;             // fused kernel: 2 x ~110 KiB of shared memory per SM
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     Ctl *ctl = reinterpret_cast<Ctl *>(smem + kCtlOff);
 
     const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
-    if (threadIdx.x == 0) {
+    if (warp == 0 && lane == 0) {
         mbar_init(&ctl->in_full, 1);
         for (int i = 0; i < kRing; i++) {
             mbar_init(&ctl->full[i], 1);
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     uint32_t in_phase = 0;
     for (uint32_t it = 0;; it++) {
         BlockDesc *dsc = &ctl->desc[it & 1];
-        if (threadIdx.x == 0) {
+        if (warp == 0 && lane == 0) {
             claim_block(p, dsc, pace);
             ctl->block_end_seq = 0xffffffffu;
             ctl->nseg = 0;
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                     const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the old block before the async write
                     mbar_arrive_expect_tx(&ctl->in_full, bytes);
-                    bulk_load(in, src, bytes, &ctl->in_full);
+                    for (uint32_t o = 0; o < bytes; o += kLoadPiece)  // several copies in flight: the pieces stream in parallel
+                        bulk_load(in + o, src + o, min(kLoadPiece, bytes - o), &ctl->in_full);
                 }
                 // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty".  (Warp 1's first table access
                 // follows warp 0's first table phase through the token, so it sees the cleared table.)
