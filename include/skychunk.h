@@ -35,7 +35,7 @@ extern "C" {
 #define SKY_API
 #endif
 
-#define SKY_ABI_VERSION 1
+#define SKY_ABI_VERSION 2
 
 /* error codes */
 #define SKY_OK 0
@@ -46,16 +46,23 @@ extern "C" {
 #define SKY_E_BUSY (-5)      /* all slots hold un-waited tickets */
 #define SKY_E_TICKET (-6)    /* unknown / already consumed ticket */
 #define SKY_E_NOMEM (-7)
+#define SKY_E_NOKEY (-8)     /* SKY_F_E2EE without sky_set_e2ee_key() / without nonces */
 
-/* stage selection for sky_process_device (0 = both) */
+/* stage selection (0 = LZ4 + MD5).  SKY_F_MD5 alone is the reference's `compress: false` (gateway_daemon.py:235,
+ * gateway_operator.py:358): the chunk is digested and passes through uncompressed. */
 #define SKY_F_LZ4 1u
 #define SKY_F_MD5 2u
-/* keep the SM sub-partition that hosts an MD5 warp free of LZ4 warps (applied automatically when the batch has
- * at most one MD5 group per SM, i.e. <= 32 x SM-count chunks; the flag forces it for larger batches) */
+/* accepted and ignored since ABI 2 (round 1 kept an SM sub-partition free for each MD5 warp; digest groups now run in
+ * CTAs of their own) */
 #define SKY_F_MD5_EXCLUSIVE 4u
 /* do not pace LZ4 work to the MD5 lanes' progress (pacing lets the lanes read the input from L2; sky_submit always
  * runs unpaced so that the kernels of different slots overlap) */
 #define SKY_F_NO_PACING 8u
+/* end-to-end encryption behind the frame (sky_submit_flags / sky_decode_flags): every payload becomes PyNaCl's
+ * SecretBox.encrypt() message  nonce(24) | tag(16) | ciphertext  (XSalsa20-Poly1305), as GatewaySender does with
+ * e2ee_key_bytes (gateway_operator.py:183-186, :362-364) and the receiver undoes (gateway_receiver.py:191-193). */
+#define SKY_F_E2EE 16u
+#define SKY_BOX_OVERHEAD 40u
 
 typedef struct sky_ctx sky_ctx;
 
@@ -95,6 +102,15 @@ SKY_API int sky_pinned_free(void *p);
 SKY_API int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
                const uint64_t *dst_cap, uint64_t *ticket);
 SKY_API int sky_wait(sky_ctx *ctx, uint64_t ticket, uint64_t *out_len, uint8_t *md5, float *kernel_ms);
+/* sky_submit with stage flags.  flags = SKY_F_MD5: digests only (dst / dst_cap may be NULL, out_len comes back 0: the
+ *   caller forwards its own input bytes, is_compressed = False).  | SKY_F_E2EE: what comes back in dst[i] is the sealed
+ *   box of the frame (or of the raw chunk when SKY_F_LZ4 is off), out_len[i] = its length = payload + SKY_BOX_OVERHEAD,
+ *   dst_cap[i] >= sky_box_bound(src_len[i]); nonces = 24 bytes per chunk chosen by the caller (nacl.utils.random(24)).
+ *   The key is the ctx's (sky_set_e2ee_key; key32 = NULL switches E2EE off). */
+SKY_API int sky_submit_flags(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
+                     const uint64_t *dst_cap, uint32_t flags, const uint8_t *nonces, uint64_t *ticket);
+SKY_API int sky_set_e2ee_key(sky_ctx *ctx, const uint8_t *key32);
+SKY_API uint64_t sky_box_bound(uint64_t n); /* sky_frame_bound(n) + SKY_BOX_OVERHEAD */
 
 /* ---- device-resident path (kernel metric; inputs already in HBM) ------------------------------
  * Chunk i is d_src[src_off[i] .. +src_len[i]) ; its frame is written at d_dst + dst_off[i]
@@ -122,11 +138,16 @@ SKY_API int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, cons
 #define SKY_D_UNSUPPORTED (-4)
 #define SKY_D_LAYOUT (-5)
 #define SKY_D_TRUNCATED (-6)
+#define SKY_D_AUTH (-7) /* SKY_F_E2EE: the box's Poly1305 tag does not verify (nacl.exceptions.CryptoError in the reference) */
 SKY_API int sky_decode_device(sky_ctx *ctx, uint32_t n, const void *d_frames, const uint64_t *frame_off, const uint64_t *frame_len,
                       void *d_out, const uint64_t *out_off, const uint64_t *raw_len, void *stream, int32_t *status, uint8_t *md5,
                       float *kernel_ms);
 SKY_API int sky_decode(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
                const uint64_t *raw_len, int32_t *status, uint8_t *md5, float *kernel_ms);
+/* sky_decode with flags: SKY_F_E2EE = the payloads are sealed boxes; tags are checked and the boxes opened on the device
+ * before the frames are decoded (status SKY_D_AUTH for a forged / truncated box, whose bytes are never returned). */
+SKY_API int sky_decode_flags(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
+                     const uint64_t *raw_len, uint32_t flags, int32_t *status, uint8_t *md5, float *kernel_ms);
 
 /* Device-memory helpers so a host without torch can drive the device path. */
 SKY_API int sky_device_alloc(sky_ctx *ctx, uint64_t bytes, void **dptr);

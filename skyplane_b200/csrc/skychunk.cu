@@ -40,6 +40,7 @@
 #include "lz4.cuh"
 #include "lz4dec.cuh"
 #include "md5.cuh"
+#include "secretbox.cuh"
 
 namespace sky {
 
@@ -496,7 +497,7 @@ struct DecRowGate {
 // Persistent: warps 0..3 of a CTA may host an MD5 group (digest of the decoded bytes, following the decode through
 // per-block flags); every other warp (and MD5 warps once their groups are done) decodes blocks.
 __global__ void __launch_bounds__(512, 1) sky_decode_kernel(const DecParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.md5_out && warp < kMd5WarpsPerCta) {
         const uint32_t md5_slots = gridDim.x * kMd5WarpsPerCta;
@@ -559,6 +560,52 @@ __global__ void __launch_bounds__(512, 1) sky_decode_kernel(const DecParams p) {
     }
 }
 
+// ---- E2EE glue: describe one box per chunk once the frame lengths exist (they are only known on the device).
+// seal: msg = the chunk's frame (or, without LZ4, its raw bytes), box = box_base + (frame offset in the frame slab) + 64*i + 8,
+// so that box + 40 is 16-byte aligned; the nonce is copied in, out_len becomes the box length.
+__global__ void sky_box_setup_kernel(BoxChunk *bc, uint64_t *blk_base, const ChunkDesc *desc, uint32_t n, uint64_t *out_len,
+                                     const uint8_t *frame_slab, uint8_t *box_slab, const uint8_t *nonces, int use_frames) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const ChunkDesc d = desc[i];
+        BoxChunk b;
+        b.box = box_slab + (d.dst - frame_slab) + 64ull * i + 8;
+        b.msg = use_frames ? d.dst : d.src;
+        b.len = use_frames ? out_len[i] : d.len;
+        for (int k = 0; k < 24; k++) b.box[k] = nonces[24ull * i + k];
+        bc[i] = b;
+        out_len[i] = b.len + kBoxOverhead;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            blk_base[i] = acc;
+            acc += (bc[i].len + 32 + 63) / 64;
+        }
+        blk_base[n] = acc;
+    }
+}
+// open: the boxes were copied to box_slab (box i at box_off[i] + 8); the plaintext frame goes to frame_slab + frame_off[i].
+__global__ void sky_box_open_setup_kernel(BoxChunk *bc, uint64_t *blk_base, uint32_t n, const uint64_t *box_off, const uint64_t *box_len,
+                                          const uint64_t *frame_off, uint8_t *frame_slab, uint8_t *box_slab) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        BoxChunk b;
+        b.box = box_slab + box_off[i] + 8;
+        b.msg = frame_slab + frame_off[i];
+        b.len = box_len[i] >= (uint64_t)kBoxOverhead ? box_len[i] - kBoxOverhead : 0;
+        bc[i] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            blk_base[i] = acc;
+            acc += (bc[i].len + 32 + 63) / 64;
+        }
+        blk_base[n] = acc;
+    }
+}
+
 }  // namespace sky
 
 // ======================================================================================= host side
@@ -588,6 +635,15 @@ struct Slot {
     uint32_t *d_blkdone = nullptr;
     uint64_t dblocks_cap = 0;
     int32_t *h_dstatus = nullptr, *d_dstatus = nullptr;  // pinned host mirror / device array
+    // E2EE (allocated when a key is set): box slab, per-chunk box descriptors, stream-block prefix, subkeys, nonces
+    uint8_t *d_box = nullptr;
+    BoxChunk *d_bchunks = nullptr;
+    uint64_t *d_blkbase = nullptr;
+    uint32_t *d_sub = nullptr;
+    uint8_t *h_nonce = nullptr, *d_nonce = nullptr;
+    uint64_t *h_boxmeta = nullptr, *d_boxmeta = nullptr;  // open side: box_off | box_len | frame_off (3 x n)
+    int32_t *h_bstatus = nullptr, *d_bstatus = nullptr;
+    uint32_t flags = 0;
     // in-flight ticket
     bool busy = false;
     uint64_t ticket = 0;
@@ -610,6 +666,7 @@ struct sky_ctx {
     // stream, so the two directions use different copy engines and batch k's frames leave while batch k+1's
     // input arrives (per-slot streams put both directions of all slots into one in-order engine queue).
     cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+    uint8_t *d_key = nullptr;  // 32-byte SecretBox key (null: E2EE off)
     bool trace = false;           // SKYCHUNK_TRACE=1: print per-batch device timeline to stderr
     cudaEvent_t ev_base = nullptr;
 };
@@ -640,6 +697,7 @@ const char *sky_strerror(int code) {
     case SKY_E_BUSY: return "all slots busy";
     case SKY_E_TICKET: return "unknown ticket";
     case SKY_E_NOMEM: return "out of memory";
+    case SKY_E_NOKEY: return "SKY_F_E2EE without a key (sky_set_e2ee_key) or without nonces";
     default: return "unknown error";
     }
 }
@@ -725,6 +783,8 @@ static void free_slot(Slot &s) {
     cudaFree(s.d_desc); cudaFree(s.d_order); cudaFree(s.d_chain); cudaFree(s.d_counters);
     cudaFreeHost(s.h_dchunks); cudaFree(s.d_dchunks); cudaFree(s.d_dblocks); cudaFree(s.d_blkdone); cudaFreeHost(s.h_dstatus); cudaFree(s.d_dstatus); cudaFree(s.d_freed); cudaFree(s.d_progress);
     cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_scratch);
+    cudaFree(s.d_box); cudaFree(s.d_bchunks); cudaFree(s.d_blkbase); cudaFree(s.d_sub); cudaFree(s.d_nonce); cudaFreeHost(s.h_nonce);
+    cudaFree(s.d_boxmeta); cudaFreeHost(s.h_boxmeta); cudaFree(s.d_bstatus); cudaFreeHost(s.h_bstatus);
     if (s.ev_k0) cudaEventDestroy(s.ev_k0);
     if (s.ev_k1) cudaEventDestroy(s.ev_k1);
     if (s.ev_res) cudaEventDestroy(s.ev_res);
@@ -803,6 +863,7 @@ int sky_ctx_destroy(sky_ctx *ctx) {
     if (ctx->st_h2d) { cudaStreamSynchronize(ctx->st_h2d); cudaStreamDestroy(ctx->st_h2d); }
     if (ctx->st_d2h) { cudaStreamSynchronize(ctx->st_d2h); cudaStreamDestroy(ctx->st_d2h); }
     if (ctx->ev_base) cudaEventDestroy(ctx->ev_base);
+    cudaFree(ctx->d_key);
     delete ctx;
     return SKY_OK;
 }
@@ -819,6 +880,56 @@ void *sky_pinned_alloc(uint64_t bytes) {
 int sky_pinned_free(void *p) {
     if (!p) return SKY_OK;
     return cudaFreeHost(p) == cudaSuccess ? SKY_OK : SKY_E_CUDA;
+}
+
+uint64_t sky_box_bound(uint64_t n) { return sky_frame_bound(n) + kBoxOverhead; }
+
+static int alloc_box(sky_ctx *ctx, Slot &s) {
+    if (s.d_box) return SKY_OK;
+    const size_t nc = ctx->max_chunks;
+    CK(ctx, cudaMalloc(&s.d_box, ctx->out_cap + 64 * nc + 256));
+    CK(ctx, cudaMalloc(&s.d_bchunks, nc * sizeof(BoxChunk)));
+    CK(ctx, cudaMalloc(&s.d_blkbase, (nc + 1) * sizeof(uint64_t)));
+    CK(ctx, cudaMalloc(&s.d_sub, nc * 16 * sizeof(uint32_t)));
+    CK(ctx, cudaMalloc(&s.d_nonce, nc * 24));
+    CK(ctx, cudaMallocHost(&s.h_nonce, nc * 24));
+    CK(ctx, cudaMalloc(&s.d_boxmeta, 3 * nc * sizeof(uint64_t)));
+    CK(ctx, cudaMallocHost(&s.h_boxmeta, 3 * nc * sizeof(uint64_t)));
+    CK(ctx, cudaMalloc(&s.d_bstatus, nc * sizeof(int32_t)));
+    CK(ctx, cudaMallocHost(&s.h_bstatus, nc * sizeof(int32_t)));
+    return SKY_OK;
+}
+
+int sky_set_e2ee_key(sky_ctx *ctx, const uint8_t *key32) {
+    if (!ctx) return SKY_E_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!key32) {
+        cudaFree(ctx->d_key);
+        ctx->d_key = nullptr;
+        return SKY_OK;
+    }
+    if (!ctx->d_key) CK(ctx, cudaMalloc(&ctx->d_key, 32));
+    CK(ctx, cudaMemcpy(ctx->d_key, key32, 32, cudaMemcpyHostToDevice));
+    for (auto &s : ctx->slots) {
+        int rc = alloc_box(ctx, s);
+        if (rc != SKY_OK) return rc;
+    }
+    return SKY_OK;
+}
+
+// Seal the batch's frames (or raw chunks) on `st` after the fused kernel: setup -> keys -> xor -> tag.
+static int launch_seal(sky_ctx *ctx, Slot &s, cudaStream_t st, uint32_t n, uint8_t *d_dst, uint32_t flags) {
+    const int use_frames = (flags & SKY_F_LZ4) ? 1 : 0;
+    sky_box_setup_kernel<<<1, 256, 0, st>>>(s.d_bchunks, s.d_blkbase, s.d_desc, n, s.d_outlen, d_dst, s.d_box, s.d_nonce, use_frames);
+    CK(ctx, cudaGetLastError());
+    sky_box_keys_kernel<<<(n + 63) / 64, 64, 0, st>>>(s.d_bchunks, n, ctx->d_key, s.d_sub);
+    CK(ctx, cudaGetLastError());
+    sky_box_xor_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.d_bchunks, s.d_blkbase, n, s.d_sub, 0);
+    CK(ctx, cudaGetLastError());
+    sky_box_tag_kernel<<<n, kPolyThreads, 0, st>>>(s.d_bchunks, s.d_sub, 0, nullptr);
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 4;
+    return SKY_OK;
 }
 
 // Fills the slot's metadata for a batch and enqueues: meta H2D, counter reset, fused kernel, results D2H.
@@ -881,7 +992,11 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     CK(ctx, cudaGetLastError());
     CK(ctx, cudaEventRecord(s.ev_k1, st));
     ctx->launches++;
-    CK(ctx, cudaEventRecord(s.ev_res, st));  // kernel done => sizes + digests are in host memory
+    if (flags & SKY_F_E2EE) {
+        int rc = launch_seal(ctx, s, st, n, d_dst, flags);
+        if (rc != SKY_OK) return rc;
+    }
+    CK(ctx, cudaEventRecord(s.ev_res, st));  // kernel(s) done => sizes + digests are in host memory
     return SKY_OK;
 }
 
@@ -891,8 +1006,11 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
 static int issue_d2h(sky_ctx *ctx, Slot &s) {
     CK(ctx, cudaStreamWaitEvent(ctx->st_d2h, s.ev_res, 0));
     if (ctx->trace) CK(ctx, cudaEventRecord(s.ev_d0, ctx->st_d2h));
-    for (uint32_t i = 0; i < s.n; i++)
-        CK(ctx, cudaMemcpyAsync(s.dst[i], s.d_out + s.out_off[i], s.h_outlen[i], cudaMemcpyDeviceToHost, ctx->st_d2h));
+    for (uint32_t i = 0; i < s.n; i++) {
+        if (s.h_outlen[i] == 0) continue;  // MD5-only batch without E2EE: nothing comes back but the digests
+        const uint8_t *from = (s.flags & SKY_F_E2EE) ? s.d_box + s.out_off[i] + 64ull * i + 8 : s.d_out + s.out_off[i];
+        CK(ctx, cudaMemcpyAsync(s.dst[i], from, s.h_outlen[i], cudaMemcpyDeviceToHost, ctx->st_d2h));
+    }
     if (ctx->trace) CK(ctx, cudaEventRecord(s.ev_d1, ctx->st_d2h));
     CK(ctx, cudaEventRecord(s.ev_d2h, ctx->st_d2h));
     s.d2h_issued = true;
@@ -914,6 +1032,7 @@ int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, const uint64
                        void *d_dst, const uint64_t *dst_off, const uint64_t *dst_cap, uint32_t flags, void *stream,
                        uint64_t *out_len, uint8_t *md5, float *kernel_ms) {
     if (!ctx || n == 0 || !src_off || !src_len || !dst_off || !dst_cap || !d_dst) return SKY_E_INVALID;
+    if (flags & SKY_F_E2EE) return SKY_E_INVALID;  // boxes are a host-path feature (sky_submit_flags)
     if (n > ctx->max_chunks) return SKY_E_CAPACITY;
     if ((reinterpret_cast<uintptr_t>(d_src) & 15) || (reinterpret_cast<uintptr_t>(d_dst) & 15)) return SKY_E_INVALID;
     for (uint32_t i = 0; i < n; i++) {
@@ -936,7 +1055,17 @@ int sky_process_device(sky_ctx *ctx, uint32_t n, const void *d_src, const uint64
 
 int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
                const uint64_t *dst_cap, uint64_t *ticket) {
-    if (!ctx || n == 0 || !src || !src_len || !dst || !dst_cap || !ticket) return SKY_E_INVALID;
+    return sky_submit_flags(ctx, n, src, src_len, dst, dst_cap, 0, nullptr, ticket);
+}
+
+int sky_submit_flags(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t *src_len, void *const *dst,
+                     const uint64_t *dst_cap, uint32_t flags, const uint8_t *nonces, uint64_t *ticket) {
+    if (!ctx || n == 0 || !src || !src_len || !ticket) return SKY_E_INVALID;
+    if ((flags & (SKY_F_LZ4 | SKY_F_MD5)) == 0) flags |= SKY_F_LZ4 | SKY_F_MD5;
+    const bool e2ee = (flags & SKY_F_E2EE) != 0, frames = (flags & SKY_F_LZ4) != 0;
+    const bool returns_data = frames || e2ee;  // MD5-only without E2EE: only digests come back
+    if (returns_data && (!dst || !dst_cap)) return SKY_E_INVALID;
+    if (e2ee && (!ctx->d_key || !nonces)) return SKY_E_NOKEY;
     if (n > ctx->max_chunks) return SKY_E_CAPACITY;
     Slot *sp = nullptr;
     for (auto &s : ctx->slots)
@@ -949,7 +1078,10 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
     uint64_t ip = 0, op = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (src_len[i] && !src[i]) return SKY_E_INVALID;
-        if (!dst[i] || dst_cap[i] < sky_frame_bound(src_len[i])) return SKY_E_CAPACITY;
+        if (returns_data) {
+            const uint64_t need = (frames ? sky_frame_bound(src_len[i]) : src_len[i]) + (e2ee ? kBoxOverhead : 0);
+            if (!dst[i] || dst_cap[i] < need) return SKY_E_CAPACITY;
+        }
         in_off[i] = ip;
         out_off[i] = op;
         ip += round16(src_len[i]);
@@ -963,13 +1095,18 @@ int sky_submit(sky_ctx *ctx, uint32_t n, const void *const *src, const uint64_t 
     // No MD5 pacing on the host path: paced LZ4 warps keep every CTA resident for the whole MD5 chain (tens of
     // ms), which would serialise the kernels of different slots; unpaced, a batch's LZ4 CTAs retire in a few ms
     // and the next slot's kernel overlaps this one's MD5 tail.
-    int rc = launch_batch(ctx, s, s.stream, ctx->st_h2d, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), SKY_F_NO_PACING);
+    if (e2ee) {
+        memcpy(s.h_nonce, nonces, 24ull * n);
+        CK(ctx, cudaMemcpyAsync(s.d_nonce, s.h_nonce, 24ull * n, cudaMemcpyHostToDevice, ctx->st_h2d));
+    }
+    s.flags = flags;
+    int rc = launch_batch(ctx, s, s.stream, ctx->st_h2d, n, s.d_in, in_off.data(), src_len, s.d_out, out_off.data(), flags | SKY_F_NO_PACING);
     if (rc != SKY_OK) return rc;
     s.busy = true;
     s.d2h_issued = false;
     s.ticket = ctx->next_ticket++;
     s.n = n;
-    s.dst.assign(dst, dst + n);
+    if (returns_data) s.dst.assign(dst, dst + n); else s.dst.assign(n, nullptr);
     s.out_off.swap(out_off);
     *ticket = s.ticket;
     return SKY_OK;
@@ -1128,14 +1265,21 @@ int sky_decode_device(sky_ctx *ctx, uint32_t n, const void *d_frames, const uint
 
 int sky_decode(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
                const uint64_t *raw_len, int32_t *status, uint8_t *md5, float *kernel_ms) {
+    return sky_decode_flags(ctx, n, frames, frame_len, dst, raw_len, 0, status, md5, kernel_ms);
+}
+
+int sky_decode_flags(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64_t *frame_len, void *const *dst,
+                     const uint64_t *raw_len, uint32_t flags, int32_t *status, uint8_t *md5, float *kernel_ms) {
     if (!ctx || n == 0 || !frames || !frame_len || !dst || !raw_len) return SKY_E_INVALID;
     if (n > ctx->max_chunks) return SKY_E_CAPACITY;
     Slot &s = ctx->slots[0];
     if (s.busy) return SKY_E_BUSY;
     if (!s.d_in) return SKY_E_INVALID;  // ctx created without slabs
+    const bool e2ee = (flags & SKY_F_E2EE) != 0;
+    if (e2ee && !ctx->d_key) return SKY_E_NOKEY;
     CK(ctx, cudaSetDevice(ctx->device));
     // roles swap on the way back: frames (<= bound) go into the frame slab, decoded bytes into the input slab
-    std::vector<uint64_t> f_off(n), o_off(n);
+    std::vector<uint64_t> f_off(n), o_off(n), f_len(frame_len, frame_len + n);
     uint64_t fp = 0, op = 0;
     for (uint32_t i = 0; i < n; i++) {
         if (!frames[i] || (raw_len[i] && !dst[i])) return SKY_E_INVALID;
@@ -1145,10 +1289,41 @@ int sky_decode(sky_ctx *ctx, uint32_t n, const void *const *frames, const uint64
         op += round16(raw_len[i]);
     }
     if (fp > ctx->out_cap || op > ctx->in_cap) return SKY_E_CAPACITY;
-    for (uint32_t i = 0; i < n; i++)
-        CK(ctx, cudaMemcpyAsync(s.d_out + f_off[i], frames[i], frame_len[i], cudaMemcpyHostToDevice, s.stream));
-    int rc = sky_decode_device(ctx, n, s.d_out, f_off.data(), frame_len, s.d_in, o_off.data(), raw_len, s.stream, status, md5, kernel_ms);
+    if (e2ee) {
+        // the payloads are boxes (nonce | tag | ciphertext): check the tags, decrypt into the frame slab, then decode as usual
+        int rc = alloc_box(ctx, s);
+        if (rc != SKY_OK) return rc;
+        for (uint32_t i = 0; i < n; i++) {
+            s.h_boxmeta[i] = f_off[i] + 64ull * i;
+            s.h_boxmeta[n + i] = frame_len[i];
+            s.h_boxmeta[2 * n + i] = f_off[i];
+            CK(ctx, cudaMemcpyAsync(s.d_box + f_off[i] + 64ull * i + 8, frames[i], frame_len[i], cudaMemcpyHostToDevice, s.stream));
+            f_len[i] = frame_len[i] >= (uint64_t)kBoxOverhead ? frame_len[i] - kBoxOverhead : 0;
+        }
+        CK(ctx, cudaMemcpyAsync(s.d_boxmeta, s.h_boxmeta, 3ull * n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        sky_box_open_setup_kernel<<<1, 256, 0, s.stream>>>(s.d_bchunks, s.d_blkbase, n, s.d_boxmeta, s.d_boxmeta + n, s.d_boxmeta + 2 * n, s.d_out, s.d_box);
+        CK(ctx, cudaGetLastError());
+        sky_box_keys_kernel<<<(n + 63) / 64, 64, 0, s.stream>>>(s.d_bchunks, n, ctx->d_key, s.d_sub);
+        CK(ctx, cudaGetLastError());
+        sky_box_tag_kernel<<<n, kPolyThreads, 0, s.stream>>>(s.d_bchunks, s.d_sub, 1, s.d_bstatus);
+        CK(ctx, cudaGetLastError());
+        sky_box_xor_kernel<<<ctx->sm_count * 8, 256, 0, s.stream>>>(s.d_bchunks, s.d_blkbase, n, s.d_sub, 1);
+        CK(ctx, cudaGetLastError());
+        CK(ctx, cudaMemcpyAsync(s.h_bstatus, s.d_bstatus, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        ctx->launches += 4;
+    } else {
+        for (uint32_t i = 0; i < n; i++)
+            CK(ctx, cudaMemcpyAsync(s.d_out + f_off[i], frames[i], frame_len[i], cudaMemcpyHostToDevice, s.stream));
+    }
+    int rc = sky_decode_device(ctx, n, s.d_out, f_off.data(), f_len.data(), s.d_in, o_off.data(), raw_len, s.stream, status, md5, kernel_ms);
     if (rc != SKY_OK) return rc;
+    if (e2ee) {
+        for (uint32_t i = 0; i < n; i++)
+            if (s.h_bstatus[i] != 0 || frame_len[i] < (uint64_t)kBoxOverhead) {  // forged or truncated box: never hand its bytes out
+                s.h_dstatus[i] = SKY_D_AUTH;
+                if (status) status[i] = SKY_D_AUTH;
+            }
+    }
     for (uint32_t i = 0; i < n; i++)
         if (raw_len[i] && s.h_dstatus[i] == 0)
             CK(ctx, cudaMemcpyAsync(dst[i], s.d_in + o_off[i], raw_len[i], cudaMemcpyDeviceToHost, s.stream));

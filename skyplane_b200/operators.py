@@ -130,9 +130,20 @@ class GatewayCompressHash(GatewayOperator):
         keep_frames_on_disk: bool = True,
         read_threads: int = 8,
         ingest_read_local: bool = True,
+        e2ee_key_bytes: Optional[bytes] = None,
+        sink=None,
     ):
+        """use_compression / e2ee_key_bytes: GatewaySender's arguments of the same name (gateway_operator.py:154-168):
+        ``use_compression=False`` digests the chunk and lets it pass through uncompressed (``is_compressed=False``);
+        ``e2ee_key_bytes`` seals every payload in a SecretBox on the GPU.
+        sink: ``callable(worker_id) -> socket``, called once in each worker.  With a sink the worker sends every payload
+        straight from the pinned staging slot (``wire.send_results``: WireProtocolHeader + payload, no intermediate bytes
+        object, no frame file) -- the tail of ``GatewaySender.process`` (gateway_operator.py:367-402)."""
         super().__init__(handle, region, input_queue, output_queue, error_event, error_queue, chunk_store, n_processes)
-        self.use_compression = use_compression
+        self.use_compression = True if use_compression is None else bool(use_compression)
+        self.e2ee_key_bytes = e2ee_key_bytes
+        self.sink = sink
+        self._sock = None
         self.max_batch_chunks = max_batch_chunks
         self.max_batch_bytes = max_batch_bytes
         self.n_gpus = n_gpus
@@ -157,9 +168,25 @@ class GatewayCompressHash(GatewayOperator):
 
                 bind_to_gpu(device)  # pinned staging buffers on the GPU's own socket
             self._stage = ChunkStage(device, self.max_batch_bytes, self.max_batch_chunks, n_slots=2)
+            if self.e2ee_key_bytes is not None:
+                self._stage.set_e2ee_key(self.e2ee_key_bytes)
         return self._stage
 
+    def _grow_stage(self, n: int):
+        """A chunk larger than the staging slots (e.g. a 64 MiB multipart part behind a small max_batch_bytes): rebuild the
+        stage with room for it instead of stopping the gateway.  Only called while no batch is in flight."""
+        if self._stage is not None:
+            self._stage.close()
+            self._stage = None
+        self.max_batch_bytes = max(self.max_batch_bytes, (n + (1 << 20)) & ~((1 << 20) - 1))
+
     def worker_exit(self, worker_id: int):
+        if self._sock is not None:
+            try:
+                self._sock.close()
+            except OSError:
+                pass
+            self._sock = None
         if self._readers is not None:
             self._readers.shutdown(wait=True)
             self._readers = None
@@ -218,7 +245,12 @@ class GatewayCompressHash(GatewayOperator):
             n = chunk.chunk_length_bytes
             if n > stage.max_batch_bytes:
                 stage.release(slot)
-                raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds the stage's max_batch_bytes")
+                if len(stage._free) < len(stage._slots):  # batches in flight: come back when they have been collected
+                    return None, [], [], list(range(len(reqs)))
+                self._grow_stage(n)
+                if n > self._get_stage().max_batch_bytes:
+                    raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds what the stage can be grown to")
+                return self._launch(reqs)
             path, offset, ready = self._source_of(r)
             if not ready:
                 not_ready.append(i)
@@ -237,7 +269,7 @@ class GatewayCompressHash(GatewayOperator):
                 stage.release(slot)
                 return None, [], [j[0] for j in jobs] + not_ready, leftover
             launched = [j[0] for j in jobs]
-            stage.launch(slot)
+            stage.launch(slot, compress=self.use_compression, encrypt=self.e2ee_key_bytes is not None)
             return slot, launched, not_ready, leftover
         stage.release(slot)
         if leftover:
@@ -245,15 +277,26 @@ class GatewayCompressHash(GatewayOperator):
         return None, [], not_ready, leftover
 
     def _finish(self, slot, reqs: List[ChunkRequest]):
-        """Collect a launched batch: sets md5_hash, writes frames, attaches the size metadata."""
+        """Collect a launched batch: sets md5_hash, hands the payloads on (socket sink, or payload files), attaches the
+        size metadata.  The slot's pinned views stay valid until the slot is reused, i.e. until this returns."""
         results = self._get_stage().collect(slot)
         for r, res in zip(reqs, results):
-            chunk = r.chunk
-            chunk.md5_hash = res.md5
-            if self.keep_frames_on_disk:
-                with open(self.chunk_store.get_compressed_file_path(chunk.chunk_id), "wb") as f:
-                    f.write(res.frame)
+            r.chunk.md5_hash = res.md5
             r._stage_meta = {"compressed_size_bytes": res.comp_len, "uncompressed_size_bytes": res.raw_len}
+        if self.sink is not None:
+            from skyplane_b200 import wire
+
+            if self._sock is None:
+                self._sock = self.sink(self.worker_id or 0)
+            wire.send_results(self._sock, [r.chunk for r in reqs], results)
+        elif self.keep_frames_on_disk:
+            for r, res in zip(reqs, results):
+                if res.is_compressed or res.is_encrypted:  # (a plain pass-through chunk is already on disk as <id>.chunk)
+                    path = self.chunk_store.get_compressed_file_path(r.chunk.chunk_id)
+                    tmp = path.with_name(path.name + ".part")
+                    with open(tmp, "wb") as f:
+                        f.write(res.frame)
+                    os.replace(tmp, path)  # readers never see a half-written payload
 
     def process_batch(self, reqs: List[ChunkRequest]) -> List[bool]:
         """Compress + hash a batch synchronously. One bool per request (False = chunk file not ready yet, retry)."""
@@ -285,6 +328,8 @@ class GatewayCompressHash(GatewayOperator):
             while self._running(worker_id):
                 try:
                     stage_free = self._stage is None or bool(self._stage._free)
+                    if backlog and inflight and max(r.chunk.chunk_length_bytes for r in backlog) > self.max_batch_bytes:
+                        stage_free = False  # an oversize chunk waits for the stage to drain, then the stage is rebuilt
                     if stage_free:
                         room = self.max_batch_chunks - len(backlog)
                         fresh = self.input_queue.get_batch_nowait(room, self.handle) if room > 0 else []
@@ -328,20 +373,25 @@ class ChecksumMismatchException(Exception):
 class GatewayDecompressVerify(GatewayOperator):
     """Receiving side: what gateway_receiver.py:191-233 does after the socket read.
 
-    ``<chunk_id>.chunk.lz4`` (the wire payload) -> LZ4 frame decode on the GPU -> ``<chunk_id>.chunk`` of exactly
-    ``chunk_length_bytes`` bytes (the size check at gateway_receiver.py:213-218), and -- closing the reference's
-    "# todo check hash" (gateway_receiver.py:231) -- the digest of the decoded bytes is compared with
-    ``chunk.md5_hash`` when the sender supplied one.  A corrupt frame or a digest mismatch raises, which stops the
-    gateway through ``error_event`` like any other operator failure."""
+    ``<chunk_id>.chunk.lz4`` (the wire payload) -> [SecretBox open on the GPU] -> LZ4 frame decode on the GPU ->
+    ``<chunk_id>.chunk`` of exactly ``chunk_length_bytes`` bytes (the size check at gateway_receiver.py:213-218), and --
+    closing the reference's "# todo check hash" (gateway_receiver.py:231) -- the digest of the decoded bytes is compared
+    with ``chunk.md5_hash`` when the sender supplied one.  Requests are drained in batches (one decode launch per batch);
+    a payload that is missing or still being written is re-queued like GatewayWaitReceiver does (gateway_operator.py:131-150);
+    a complete but corrupt payload, a forged box or a digest mismatch raises, which stops the gateway through
+    ``error_event`` like any other operator failure."""
 
     def __init__(self, *args, max_batch_chunks: int = 64, max_batch_bytes: int = 512 << 20, n_gpus: Optional[int] = None,
-                 remove_frames: bool = True, **kwargs):
+                 remove_frames: bool = True, e2ee_key_bytes: Optional[bytes] = None, stale_retries: int = 50, **kwargs):
         super().__init__(*args, **kwargs)
         self.max_batch_chunks = max_batch_chunks
         self.max_batch_bytes = max_batch_bytes
         self.n_gpus = n_gpus
         self.remove_frames = remove_frames
+        self.e2ee_key_bytes = e2ee_key_bytes
+        self.stale_retries = stale_retries  # re-queues of an unchanged, undecodable payload before it counts as corrupt
         self._stage = None
+        self._seen = {}  # chunk_id -> (payload size at the last attempt, attempts at that size)
 
     def _get_stage(self):
         if self._stage is None:
@@ -352,6 +402,8 @@ class GatewayDecompressVerify(GatewayOperator):
             if ngpu <= 0:
                 raise native.SkyChunkError(native.SKY_E_NOGPU, "GatewayDecompressVerify needs a CUDA device; there is no CPU fallback")
             self._stage = ChunkStage((self.worker_id or 0) % ngpu, self.max_batch_bytes, self.max_batch_chunks, n_slots=1)
+            if self.e2ee_key_bytes is not None:
+                self._stage.set_e2ee_key(self.e2ee_key_bytes)
         return self._stage
 
     def worker_exit(self, worker_id: int):
@@ -360,22 +412,86 @@ class GatewayDecompressVerify(GatewayOperator):
             self._stage = None
 
     def process(self, chunk_req: ChunkRequest, *args) -> bool:
+        return self.process_batch([chunk_req])[0]
+
+    def _still_arriving(self, chunk_id: str, size: int) -> bool:
+        """True while an undecodable payload may simply be incomplete: its size changed since the last look, or it has not
+        been looked at `stale_retries` times yet (each re-queue waits 0.1 s)."""
+        last, tries = self._seen.get(chunk_id, (None, 0))
+        tries = tries + 1 if last == size else 1
+        self._seen[chunk_id] = (size, tries)
+        return tries <= self.stale_retries
+
+    def process_batch(self, reqs: List[ChunkRequest]) -> List[bool]:
+        """One bool per request: False = payload not there / not complete yet (re-queue)."""
         from skyplane_b200 import native
 
-        chunk = chunk_req.chunk
-        fpath = self.chunk_store.get_compressed_file_path(chunk.chunk_id)
-        if not fpath.exists():
-            return False  # payload not received yet: retry (GatewayWaitReceiver semantics, gateway_operator.py:131-150)
-        frame = fpath.read_bytes()
-        (data, digest, status), = self._get_stage().decode([frame], [chunk.chunk_length_bytes])
-        if status != 0:
-            raise ValueError(f"chunk {chunk.chunk_id}: LZ4 frame rejected ({native.D_NAMES.get(status, status)})")
-        if chunk.md5_hash is not None and bytes(chunk.md5_hash) != digest:
-            raise ChecksumMismatchException(f"chunk {chunk.chunk_id}: md5 {digest.hex()} != expected {bytes(chunk.md5_hash).hex()}")
-        with open(self.chunk_store.get_chunk_file_path(chunk.chunk_id), "wb") as f:
-            f.write(data)
-        if chunk.md5_hash is None:
+        ok = [False] * len(reqs)
+        ready, frames = [], []
+        total = 0
+        for i, r in enumerate(reqs):
+            fpath = self.chunk_store.get_compressed_file_path(r.chunk.chunk_id)
+            try:
+                frame = fpath.read_bytes()
+            except FileNotFoundError:
+                continue  # payload not received yet: retry
+            if total + len(frame) + r.chunk.chunk_length_bytes > self.max_batch_bytes and ready:
+                continue  # next batch
+            total += len(frame) + r.chunk.chunk_length_bytes
+            ready.append(i)
+            frames.append(frame)
+        if not ready:
+            return ok
+        encrypted = self.e2ee_key_bytes is not None
+        out = self._get_stage().decode(frames, [reqs[i].chunk.chunk_length_bytes for i in ready], encrypted=encrypted)
+        for i, frame, (data, digest, status) in zip(ready, frames, out):
+            chunk = reqs[i].chunk
+            if status in (native.D_TRUNCATED, native.D_BAD_HEADER, native.D_AUTH) and self._still_arriving(chunk.chunk_id, len(frame)):
+                continue  # a writer may still be appending (a short box fails authentication, a short frame is truncated)
+            if status != 0:
+                raise ValueError(f"chunk {chunk.chunk_id}: payload rejected ({native.D_NAMES.get(status, status)})")
+            want = chunk.md5_hash
+            if isinstance(want, str):  # a digest that crossed a JSON hop un-normalised
+                want = bytes.fromhex(want)
+            if want is not None and bytes(want) != digest:
+                raise ChecksumMismatchException(f"chunk {chunk.chunk_id}: md5 {digest.hex()} != expected {bytes(want).hex()}")
+            path = self.chunk_store.get_chunk_file_path(chunk.chunk_id)
+            tmp = path.with_name(path.name + ".part")
+            with open(tmp, "wb") as f:
+                f.write(data)
+            os.replace(tmp, path)
             chunk.md5_hash = digest  # lets the upload step send Content-MD5 (gateway_operator.py:640)
-        if self.remove_frames:
-            fpath.unlink(missing_ok=True)
-        return True
+            self._seen.pop(chunk.chunk_id, None)
+            if self.remove_frames:
+                self.chunk_store.get_compressed_file_path(chunk.chunk_id).unlink(missing_ok=True)
+            ok[i] = True
+        return ok
+
+    def worker_loop(self, worker_id: int, *args):
+        """Batch-draining loop with the reference's logging / error conventions (gateway_operator.py:79-115)."""
+        self.worker_id = worker_id
+        try:
+            while self._running(worker_id):
+                try:
+                    reqs = self.input_queue.get_batch_nowait(self.max_batch_chunks, self.handle)
+                    if not reqs:
+                        time.sleep(0.001)
+                        continue
+                    for r in reqs:
+                        self.chunk_store.log_chunk_state(r, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
+                    done = self.process_batch(reqs)
+                    for r, good in zip(reqs, done):
+                        if good:
+                            self.chunk_store.log_chunk_state(r, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id)
+                            if self.output_queue is not None:
+                                self.output_queue.put(r)
+                    retry = [r for r, good in zip(reqs, done) if not good]
+                    if retry:
+                        if len(retry) == len(reqs):
+                            time.sleep(0.1)  # nothing was ready: the reference's re-queue pause (gateway_operator.py:103-106)
+                        for r in retry:
+                            self.input_queue.put(r)
+                except Exception as e:
+                    self._fail(worker_id, e)
+        finally:
+            self.worker_exit(worker_id)

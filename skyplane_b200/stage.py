@@ -23,10 +23,13 @@ BytesLike = Union[bytes, bytearray, memoryview]
 class StageResult:
     """What the sender needs for one chunk (gateway_operator.py:367-372)."""
 
-    frame: memoryview  # LZ4 frame bytes (view into the slot's pinned output; valid until the slot is reused)
+    frame: memoryview  # wire payload (view into the slot's pinned memory; valid until the slot is reused): the LZ4 frame,
+    #                    or the chunk itself when compression is off, sealed in a SecretBox when E2EE is on
     md5: bytes  # 16 raw bytes == hashlib.md5(chunk).digest()
     raw_len: int  # WireProtocolHeader.raw_data_len
-    comp_len: int  # WireProtocolHeader.data_len (before optional encryption)
+    comp_len: int  # WireProtocolHeader.data_len (length of `frame`)
+    is_compressed: bool = True  # WireProtocolHeader.is_compressed
+    is_encrypted: bool = False
 
     def frame_bytes(self) -> bytes:
         return bytes(self.frame)
@@ -45,10 +48,11 @@ class _Slot:
         self.in_used = 0
         self.out_used = 0
         self.ticket: Optional[int] = None
+        self.flags = 0
 
     def reserve(self, n: int) -> memoryview:
         """Reserve room for an n-byte chunk; returns the writable pinned view to fill."""
-        bound = native.frame_bound(n)
+        bound = native.frame_bound(n) + native.BOX_OVERHEAD  # (room for the SecretBox nonce + tag when E2EE is on)
         if self.in_used + native.round16(n) > self.inp.nbytes or self.out_used + native.round16(bound) > self.out.nbytes:
             raise native.SkyChunkError(native.SKY_E_CAPACITY, "batch exceeds the stage's staging buffers")
         off = self.in_used
@@ -68,7 +72,7 @@ class ChunkStage:
         self.max_chunks = max_chunks
         self.max_batch_bytes = max_batch_bytes
         in_bytes = native.round16(max_batch_bytes) + 16 * max_chunks
-        out_bytes = max_batch_bytes + 4 * (max_batch_bytes // 65536 + 1) + 64 * max_chunks
+        out_bytes = max_batch_bytes + 4 * (max_batch_bytes // 65536 + 1) + 128 * max_chunks
         self._slots = [_Slot(in_bytes, out_bytes) for _ in range(n_slots)]
         self._free = list(self._slots)
 
@@ -90,7 +94,7 @@ class ChunkStage:
         return (
             len(slot.lens) < self.max_chunks
             and slot.in_used + native.round16(n) <= slot.inp.nbytes
-            and slot.out_used + native.round16(native.frame_bound(n)) <= slot.out.nbytes
+            and slot.out_used + native.round16(native.frame_bound(n) + native.BOX_OVERHEAD) <= slot.out.nbytes
         )
 
     def add_bytes(self, slot: _Slot, data: BytesLike) -> int:
@@ -116,29 +120,44 @@ class ChunkStage:
             raise AssertionError(f"chunk file {path} has size != {length}")
         return len(slot.lens) - 1
 
-    def launch(self, slot: _Slot) -> _Slot:
+    def set_e2ee_key(self, key: Optional[bytes]):
+        """SecretBox key (32 bytes) for encrypt=True batches / decode(encrypted=True); None switches E2EE off."""
+        self.ctx.set_e2ee_key(key)
+        self._has_key = key is not None
+
+    def launch(self, slot: _Slot, compress: bool = True, encrypt: bool = False, nonces: Optional[bytes] = None) -> _Slot:
+        """compress=False is the reference's `compress: false` (digest only, the chunk passes through);
+        encrypt=True seals every payload with the stage's key (nonces: 24 bytes per chunk, default os.urandom)."""
         if not slot.lens:
             raise ValueError("empty batch")
         base_in, base_out = slot.inp.addr, slot.out.addr
         src = [base_in + o for o in slot.in_off]
-        dst = [base_out + o for o in slot.out_off]
-        caps = [native.frame_bound(n) for n in slot.lens]
-        slot.ticket = self.ctx.submit(src, slot.lens, dst, caps)
+        flags = native.F_MD5 | (native.F_LZ4 if compress else 0) | (native.F_E2EE if encrypt else 0)
+        if encrypt and nonces is None:
+            nonces = os.urandom(24 * len(slot.lens))  # what nacl.utils.random(24) draws per message
+        if compress or encrypt:
+            dst = [base_out + o for o in slot.out_off]
+            caps = [(native.frame_bound(n) if compress else n) + (native.BOX_OVERHEAD if encrypt else 0) for n in slot.lens]
+        else:
+            dst = caps = None
+        slot.flags = flags
+        slot.ticket = self.ctx.submit(src, slot.lens, dst, caps, flags, nonces)
         return slot
 
     def collect(self, slot: _Slot) -> List[StageResult]:
         out_lens, digests, self.last_kernel_ms = self.ctx.wait(slot.ticket)
-        res = [
-            StageResult(frame=slot.out.view[o : o + cl], md5=dg, raw_len=n, comp_len=cl)
-            for o, cl, dg, n in zip(slot.out_off, out_lens, digests, slot.lens)
-        ]
+        comp, enc = bool(slot.flags & native.F_LZ4), bool(slot.flags & native.F_E2EE)
+        res = []
+        for io, o, cl, dg, n in zip(slot.in_off, slot.out_off, out_lens, digests, slot.lens):
+            payload = slot.out.view[o : o + cl] if (comp or enc) else slot.inp.view[io : io + n]
+            res.append(StageResult(frame=payload, md5=dg, raw_len=n, comp_len=len(payload), is_compressed=comp, is_encrypted=enc))
         slot.ticket = None
         self._free.append(slot)
         return res
 
     # ------------------------------------------------------------------ sync convenience
-    def process(self, chunks: Sequence[BytesLike]) -> List[StageResult]:
-        """Compress + hash a list of in-memory chunks; frames are returned as independent bytes."""
+    def process(self, chunks: Sequence[BytesLike], compress: bool = True, encrypt: bool = False, nonces: Optional[bytes] = None) -> List[StageResult]:
+        """Compress + hash (+ seal) a list of in-memory chunks; payloads are returned as independent bytes."""
         out: List[StageResult] = []
         i = 0
         while i < len(chunks):
@@ -150,15 +169,17 @@ class ChunkStage:
             if j == i:
                 self.release(slot)
                 raise native.SkyChunkError(native.SKY_E_CAPACITY, f"chunk of {memoryview(chunks[i]).nbytes} bytes exceeds max_batch_bytes")
-            self.launch(slot)
+            self.launch(slot, compress, encrypt, nonces[24 * i : 24 * j] if nonces is not None else None)
             for r in self.collect(slot):
-                out.append(StageResult(frame=memoryview(bytes(r.frame)), md5=r.md5, raw_len=r.raw_len, comp_len=r.comp_len))
+                out.append(StageResult(frame=memoryview(bytes(r.frame)), md5=r.md5, raw_len=r.raw_len, comp_len=r.comp_len,
+                                       is_compressed=r.is_compressed, is_encrypted=r.is_encrypted))
             i = j
         return out
 
     # ------------------------------------------------------------------ receiver side
-    def decode(self, frames: Sequence[BytesLike], raw_lens: Sequence[int]):
-        """Decode LZ4 frames and digest the decoded bytes (gateway_receiver.py:195-201 + the missing hash check).
+    def decode(self, frames: Sequence[BytesLike], raw_lens: Sequence[int], encrypted: bool = False):
+        """Decode LZ4 frames and digest the decoded bytes (gateway_receiver.py:195-201 + the missing hash check);
+        encrypted=True: the payloads are SecretBox messages, opened on the device first (gateway_receiver.py:191-193).
         -> list of (data: bytes | None, md5: bytes, status: int); data is None when status != 0."""
         out = []
         i = 0
@@ -182,7 +203,8 @@ class ChunkStage:
                 raise native.SkyChunkError(native.SKY_E_CAPACITY, "frame exceeds the stage's staging buffers")
             lens = [memoryview(frames[k]).nbytes for k in range(i, j)]
             raws = list(raw_lens[i:j])
-            st, dg, self.last_kernel_ms = self.ctx.decode([slot.out.addr + o for o in f_off], lens, [slot.inp.addr + o for o in o_off], raws)
+            st, dg, self.last_kernel_ms = self.ctx.decode([slot.out.addr + o for o in f_off], lens, [slot.inp.addr + o for o in o_off], raws,
+                                                          native.F_E2EE if encrypted else 0)
             for k in range(j - i):
                 data = bytes(slot.inp.view[o_off[k] : o_off[k] + raws[k]]) if st[k] == 0 else None
                 out.append((data, dg[k], st[k]))

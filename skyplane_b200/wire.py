@@ -5,7 +5,8 @@ Sender side replaces the tail of ``GatewaySender.process`` (skyplane/gateway/ope
 the stage's pinned output slot, so the frame is never copied into a Python ``bytes``.
 Receiver side replaces the read loop of ``recv_chunks`` (skyplane/gateway/operators/gateway_receiver.py:150-189):
 the payload is received directly into a caller-supplied (pinned) buffer in <= 4 MiB reads.
-The 53-byte header layout is ``WireProtocolHeader``'s (skyplane/chunk.py:95-155); E2EE is not handled here.
+The 53-byte header layout is ``WireProtocolHeader``'s (skyplane/chunk.py:95-155).  With E2EE the payload is the sealed box
+the stage produced (``data_len`` = box length, ``raw_data_len`` = original length, as gateway_operator.py:362-372 sets them).
 """
 from __future__ import annotations
 
@@ -32,7 +33,7 @@ def send_results(sock: socket.socket, chunks: Sequence[Chunk], results) -> int:
     total = 0
     n = len(chunks)
     for i, (c, r) in enumerate(zip(chunks, results)):
-        total += send_chunk(sock, c, r.frame, r.raw_len, n_chunks_left_on_socket=n - i - 1)
+        total += send_chunk(sock, c, r.frame, r.raw_len, n_chunks_left_on_socket=n - i - 1, is_compressed=getattr(r, "is_compressed", True))
     return total
 
 

@@ -19,7 +19,7 @@ from skyplane_b200 import native
 from skyplane_b200.chunk import Chunk, ChunkRequest, ChunkState, WireProtocolHeader
 from skyplane_b200.chunk_store import ChunkStore
 from skyplane_b200.gateway_queue import GatewayANDQueue, GatewayQueue
-from skyplane_b200.operators import GatewayCompressHash, GatewayOperator
+from skyplane_b200.operators import GatewayCompressHash, GatewayDecompressVerify, GatewayOperator
 from skyplane_b200.sharding import shard_indices, shard_of_chunk_id
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -191,7 +191,8 @@ def test_header_and_library_symbols_agree():
     out = subprocess.run(["nm", "-D", "--defined-only", str(native.LIB_PATH)], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (sky_[a-z0-9_]+)", out))
     assert exported == declared
-    assert lib.sky_abi_version() == 1
+    m = re.search(r"#define SKY_ABI_VERSION (\d+)", hdr)
+    assert lib.sky_abi_version() == int(m.group(1)) == 2
 
 
 def test_frame_bound_and_strerror_without_gpu():
@@ -297,8 +298,13 @@ class _StubStage:
 
     def __init__(self, cap=4 << 20, max_chunks=4, n_slots=2):
         self.max_batch_bytes, self.max_chunks = cap, max_chunks
-        self._free = [_StubSlot(cap) for _ in range(n_slots)]
+        self._slots = [_StubSlot(cap) for _ in range(n_slots)]
+        self._free = list(self._slots)
         self.launched = 0
+        self.key = None
+
+    def set_e2ee_key(self, key):
+        self.key = key
 
     def begin(self):
         s = self._free.pop()
@@ -311,8 +317,9 @@ class _StubStage:
     def fits(self, slot, n):
         return len(slot.spans) < self.max_chunks and slot.used + n <= len(slot.buf)
 
-    def launch(self, slot):
+    def launch(self, slot, compress=True, encrypt=False, nonces=None):
         self.launched += 1
+        slot.compress, slot.encrypt = compress, encrypt
         return slot
 
     def collect(self, slot):
@@ -324,9 +331,33 @@ class _StubStage:
         out = []
         for off, n in slot.spans:
             data = bytes(slot.buf[off : off + n])
-            frame = oracle.lz4f_compress_indep(data)
-            out.append(StageResult(frame=memoryview(frame), md5=hashlib.md5(data).digest(), raw_len=n, comp_len=len(frame)))
+            frame = oracle.lz4f_compress_indep(data) if slot.compress else data
+            if slot.encrypt:
+                nonce = os.urandom(24)
+                frame = nonce + oracle.secretbox_seal(self.key, nonce, frame)
+            out.append(StageResult(frame=memoryview(frame), md5=hashlib.md5(data).digest(), raw_len=n, comp_len=len(frame),
+                                   is_compressed=slot.compress, is_encrypted=slot.encrypt))
         self._free.append(slot)
+        return out
+
+    def decode(self, frames, raw_lens, encrypted=False):
+        import hashlib
+
+        import oracle
+        from skyplane_b200 import native
+
+        out = []
+        for f, n in zip(frames, raw_lens):
+            try:
+                if encrypted:
+                    f = oracle.secretbox_open(self.key, bytes(f[:24]), bytes(f[24:])) if len(f) >= 40 else None
+                    if f is None:
+                        raise KeyError
+                data = oracle.lz4f_decode(bytes(f), n)
+                out.append((data, hashlib.md5(data).digest(), 0))
+            except (KeyError, ValueError) as e:
+                bad_auth = isinstance(e, KeyError) or "authentication" in str(e)
+                out.append((None, b"\0" * 16, native.D_AUTH if bad_auth else native.D_TRUNCATED if len(f) < 15 + n // 300 else native.D_CORRUPT))
         return out
 
     def close(self):
@@ -336,7 +367,9 @@ class _StubStage:
 class _StubbedCompressHash(GatewayCompressHash):
     def _get_stage(self):
         if self._stage is None:
-            self._stage = _StubStage()
+            self._stage = _StubStage(cap=self.max_batch_bytes)
+            if self.e2ee_key_bytes is not None:
+                self._stage.set_e2ee_key(self.e2ee_key_bytes)
         return self._stage
 
 
@@ -348,7 +381,8 @@ def test_compress_hash_worker_loop_with_stub_stage(tmp_path):
     cs = ChunkStore(tmp_path)
     qin, qout = GatewayQueue(), GatewayQueue()
     err_ev, err_q = mp.Event(), mp.Queue()
-    op = _StubbedCompressHash("ch", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=4, read_threads=2)
+    op = _StubbedCompressHash("ch", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=4, read_threads=2,
+                               max_batch_bytes=4 << 20)
     datas = {("%02x" % i) * 16: os.urandom(1000 + 37 * i) + bytes(5000) for i in range(11)}
     datas["ee" * 16] = b""  # zero-length chunk (gateway_operator.py:544-548)
     late = "dd" * 16
@@ -381,14 +415,116 @@ def test_compress_hash_worker_loop_with_stub_stage(tmp_path):
         done = [x for x in recs if x["state"] == "complete"]
         assert len(done) == len(datas)
         assert all(x["uncompressed_size_bytes"] == len(datas[x["chunk_id"]]) and x["compressed_size_bytes"] > 0 for x in done)
-        # a chunk larger than the stage can ever hold is an error -> gateway-wide stop
+        # a chunk larger than the staging slots does not stop the gateway: the stage is rebuilt with room for it
         big = "cc" * 16
         cs.get_chunk_file_path(big).write_bytes(bytes(5 << 20))
         qin.put(ChunkRequest(Chunk("k", "k", big, 5 << 20, partition_id="0")))
+        (r,) = _drain(qout, 1, timeout=20)
+        assert r.chunk.chunk_id == big and r.chunk.md5_hash == hashlib.md5(bytes(5 << 20)).digest() and not err_ev.is_set()
+    finally:
+        op.stop_workers()
+
+
+def test_compress_false_passes_chunk_through_and_sink_sends_from_the_slot(tmp_path):
+    """`compress: false` (gateway_daemon.py:235): digest only, is_compressed=False, no frame file; with a sink the payloads
+    go out as WireProtocolHeader + bytes straight from the staging slot (gateway_operator.py:367-402)."""
+    import hashlib
+    import socket
+    import threading
+
+    from skyplane_b200 import wire
+
+    cs = ChunkStore(tmp_path)
+    qin, qout = GatewayQueue(), GatewayQueue()
+    err_ev, err_q = mp.Event(), mp.Queue()
+    a, b = socket.socketpair()
+    op = _StubbedCompressHash("ch", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=4, read_threads=2,
+                               max_batch_bytes=4 << 20, use_compression=False, sink=lambda wid: a)
+    datas = {("%02x" % i) * 16: os.urandom(3000 + i) for i in range(6)}
+    for cid, d in datas.items():
+        cs.get_chunk_file_path(cid).write_bytes(d)
+    got_wire = {}
+
+    def reader():
+        buf = bytearray(1 << 20)
+        for _ in datas:
+            h, n = wire.recv_chunk(b, buf)
+            got_wire[h.chunk_id] = (h, bytes(buf[:n]))
+
+    t = threading.Thread(target=reader)
+    t.start()
+    op.start_workers()
+    try:
+        for cid, d in datas.items():
+            qin.put(ChunkRequest(Chunk("k", "k", cid, len(d), partition_id="0")))
+        got = _drain(qout, len(datas), timeout=20)
+        t.join(10)
+        assert not t.is_alive() and len(got) == len(datas)
+        for r in got:
+            d = datas[r.chunk.chunk_id]
+            h, payload = got_wire[r.chunk.chunk_id]
+            assert payload == d and h.is_compressed is False and h.data_len == h.raw_data_len == len(d)
+            assert r.chunk.md5_hash == hashlib.md5(d).digest()
+            assert not cs.get_compressed_file_path(r.chunk.chunk_id).exists()
+    finally:
+        op.stop_workers()
+        a.close(); b.close()
+
+
+class _StubbedDecompressVerify(GatewayDecompressVerify):
+    def _get_stage(self):
+        if self._stage is None:
+            self._stage = _StubStage()
+            if self.e2ee_key_bytes is not None:
+                self._stage.set_e2ee_key(self.e2ee_key_bytes)
+        return self._stage
+
+
+def test_decompress_verify_batches_waits_for_partial_payloads_and_checks_json_digests(tmp_path):
+    """a half-written payload is re-queued (not a gateway stop); a digest that crossed a JSON hop as hex is
+    compared correctly; E2EE payloads are opened first."""
+    import hashlib
+    import json
+
+    import oracle
+
+    key = bytes(range(32))
+    cs = ChunkStore(tmp_path)
+    qin, qout = GatewayQueue(), GatewayQueue()
+    err_ev, err_q = mp.Event(), mp.Queue()
+    op = _StubbedDecompressVerify("dv", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=8, e2ee_key_bytes=key)
+    datas = {("%02x" % i) * 16: (b"payload %d " % i) * 400 for i in range(5)}
+    boxes = {}
+    for cid, d in datas.items():
+        nonce = os.urandom(24)
+        boxes[cid] = nonce + oracle.secretbox_seal(key, nonce, oracle.lz4f_compress_indep(d))
+    slow = "04" * 16
+    for cid, bx in boxes.items():
+        cs.get_compressed_file_path(cid).write_bytes(bx[: len(bx) // 2] if cid == slow else bx)  # one payload is still arriving
+    op.start_workers()
+    try:
+        for cid, d in datas.items():
+            c = Chunk("k", "k", cid, len(d), partition_id="0", md5_hash=hashlib.md5(d).digest())
+            req = ChunkRequest.from_dict(json.loads(json.dumps(c.as_json_dict())))  # the gateway API's JSON hop
+            assert isinstance(req.chunk.md5_hash, bytes)
+            qin.put(req)
+        got = _drain(qout, 4, timeout=20)
+        assert len(got) == 4 and not err_ev.is_set()
+        with open(cs.get_compressed_file_path(slow), "ab") as f:  # the writer finishes
+            f.write(boxes[slow][len(boxes[slow]) // 2:])
+        got += _drain(qout, 1, timeout=20)
+        assert sorted(r.chunk.chunk_id for r in got) == sorted(datas) and not err_ev.is_set()
+        for r in got:
+            assert cs.get_chunk_file_path(r.chunk.chunk_id).read_bytes() == datas[r.chunk.chunk_id]
+        # a complete payload with a wrong digest still stops the gateway
+        bad = "0f" * 16
+        nonce = os.urandom(24)
+        cs.get_compressed_file_path(bad).write_bytes(nonce + oracle.secretbox_seal(key, nonce, oracle.lz4f_compress_indep(b"x" * 100)))
+        qin.put(ChunkRequest(Chunk("k", "k", bad, 100, partition_id="0", md5_hash=b"\1" * 16)))
         t0 = time.time()
         while not err_ev.is_set() and time.time() - t0 < 10:
             time.sleep(0.01)
-        assert err_ev.is_set() and "max_batch_bytes" in err_q.get(timeout=2)
+        assert err_ev.is_set() and "ChecksumMismatch" in err_q.get(timeout=2)
     finally:
         op.stop_workers()
 
