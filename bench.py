@@ -126,7 +126,9 @@ class CpuReference:
 
         self.use_ref = ref.available()
         self.kind = "reference" if self.use_ref else "port"
-        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        # one worker process per core this process may really use: the cgroup quota counts (a 1-GPU lease of this pool gets
+        # 16 of the host's 128 cores; 128 workers on a 16-core quota only add throttling noise)
+        self.cores = max(1, int(host_facts()["usable_cores"] + 0.5))
         self.chunk_bytes = chunk_bytes
         self.pool_chunks = pool_chunks
         self.engine = (f"liblz4 {ref.version()} LZ4F_compressFrame via ctypes (python-lz4 default prefs) + hashlib.md5"
@@ -160,7 +162,8 @@ class CpuReference:
         med = gbs[len(gbs) // 2]
         return {"value": med, "unit": UNIT, "cores": self.cores, "kind": self.kind, "passes_gbs": [round(g, 3) for g in gbs],
                 "spread": (gbs[-1] - gbs[0]) / med if med else None, "single_core_gbs": single,
-                "effective_parallelism": med / single if single else None, "ratio": self.last_ratio, "host": host_facts(),
+                "effective_parallelism": med / single if single else None, "per_core_gbs": med / self.cores, "ratio": self.last_ratio,
+                "host": host_facts(),
                 "sample": f"{n_chunks} x {self.chunk_bytes >> 20} MiB {self.workload} chunks per pass (pool of {self.pool_chunks} distinct, seeded), "
                           f"median of {passes} passes, {self.cores} worker processes, {self.engine}"}
 
@@ -271,7 +274,7 @@ def run_reference(args):
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
         "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "single_core_gbs": single,
-                         "effective_parallelism": value / single if single else None,
+                         "effective_parallelism": value / single if single else None, "per_core_gbs": value / ref.cores,
                          "step_gbs_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "host": host_facts(),
                          "sample": f"{n} x {args.chunk_mib} MiB {args.workload} chunks per step on this ONE host whatever --gpus says (pool of 16 "
                                    f"distinct, seeded), {ref.cores} worker processes, {ref.engine}"},
