@@ -71,6 +71,17 @@ class ChunkStore:
         self.log_chunk_state(chunk_request, state)
         return target.size(), True
 
+    def add_chunk_requests(self, chunk_requests, state: ChunkState = ChunkState.registered) -> None:
+        """Batch form of ``add_chunk_request`` (all requests of one partition): one queue element, one status element."""
+        reqs = list(chunk_requests)
+        if not reqs:
+            return
+        target = self.chunk_requests.get(reqs[0].chunk.partition_id)
+        if target is None:
+            raise ValueError(f"Partition {reqs[0].chunk.partition_id} does not exist in {self.chunk_requests} - was the gateway program loaded?")
+        target.put_many(reqs)
+        self.log_chunk_states(reqs, state)
+
     # -- status log -------------------------------------------------------------------------------
     def log_chunk_state(
         self,
@@ -91,6 +102,26 @@ class ChunkStore:
         if metadata:
             record.update(metadata)  # e.g. compressed_size_bytes / uncompressed_size_bytes from the B200 stage
         self.chunk_status_queue.put(record)
+
+    def log_chunk_states(self, chunk_reqs, new_status: ChunkState, worker_id: Optional[int] = None, operator_handle: Optional[str] = None,
+                         metadata: Optional[list] = None) -> None:
+        """Batch form of ``log_chunk_state``: the same records, shipped as ONE queue element (a list).  A consumer of
+        ``chunk_status_queue`` sees either a dict (the reference's form) or a list of such dicts (``iter_status_records``)."""
+        stamp = _utc_stamp()
+        records = []
+        for i, r in enumerate(chunk_reqs):
+            rec = dict(chunk_id=r.chunk.chunk_id, partition=r.chunk.partition_id, state=new_status.name, time=stamp, handle=operator_handle,
+                       worker_id=worker_id)
+            if metadata and metadata[i]:
+                rec.update(metadata[i])
+            records.append(rec)
+        if records:
+            self.chunk_status_queue.put(records)
+
+    @staticmethod
+    def iter_status_records(item):
+        """Normalise one element taken from ``chunk_status_queue`` to its records."""
+        return item if isinstance(item, list) else (item,)
 
     # -- files ------------------------------------------------------------------------------------
     def get_chunk_file_path(self, chunk_id: str) -> Path:

@@ -9,9 +9,19 @@ from __future__ import annotations
 
 import multiprocessing
 import queue as _queue
+from collections import deque
 from typing import Dict, Iterable, List
 
 DEFAULT_DEPTH = 10000  # the reference's maxsize
+
+
+class _Batch:
+    """Several requests travelling as one queue element (see GatewayQueue.put_many)."""
+
+    __slots__ = ("items",)
+
+    def __init__(self, items):
+        self.items = items
 
 
 class GatewayQueue:
@@ -20,6 +30,7 @@ class GatewayQueue:
     def __init__(self, maxsize: int = DEFAULT_DEPTH):
         self.q = multiprocessing.Queue(maxsize)
         self.handles: List[str] = []
+        self._pending = deque()  # process-local: requests of a batch already taken off the queue
 
     # -- consumers ------------------------------------------------------------------------------
     def register_handle(self, requester_handle) -> None:
@@ -29,8 +40,15 @@ class GatewayQueue:
         return self.handles
 
     def get_nowait(self, requester_handle=None):
-        """Next request or ``queue.Empty``."""
-        return self.q.get_nowait()
+        """Next request or ``queue.Empty``.  (``put_many`` ships a whole list as one queue element -- one pickle, one pipe
+        write, one wake-up instead of one per request; the consumer unpacks it here, so callers never see the difference.)"""
+        if self._pending:
+            return self._pending.popleft()
+        item = self.q.get_nowait()
+        if isinstance(item, _Batch):
+            self._pending.extend(item.items)
+            return self._pending.popleft()
+        return item
 
     def get_batch_nowait(self, max_items: int, requester_handle=None) -> list:
         """Up to ``max_items`` requests that are available right now (possibly none)."""
@@ -43,7 +61,12 @@ class GatewayQueue:
         return batch
 
     def pop(self, requester_handle=None) -> None:
-        self.q.get()
+        if self._pending:
+            self._pending.popleft()
+            return
+        item = self.q.get()
+        if isinstance(item, _Batch):
+            self._pending.extend(item.items[1:])
 
     # -- producers ------------------------------------------------------------------------------
     def put(self, chunk_req) -> None:
@@ -53,11 +76,14 @@ class GatewayQueue:
         self.q.put_nowait(chunk_req)
 
     def put_many(self, chunk_reqs: Iterable) -> None:
-        for r in chunk_reqs:
-            self.q.put(r)
+        items = list(chunk_reqs)
+        if len(items) == 1:
+            self.q.put(items[0])
+        elif items:
+            self.q.put(_Batch(items))
 
     def size(self) -> int:
-        return self.q.qsize()
+        return self.q.qsize() + len(self._pending)
 
 
 class GatewayANDQueue(GatewayQueue):
@@ -86,6 +112,11 @@ class GatewayANDQueue(GatewayQueue):
     def put(self, chunk_req) -> None:
         for private in self.q.values():
             private.put(chunk_req)
+
+    def put_many(self, chunk_reqs: Iterable) -> None:
+        items = list(chunk_reqs)
+        for private in self.q.values():
+            private.put_many(items)
 
     def put_nowait(self, chunk_req) -> None:
         raise ValueError("GatewayANDQueue cannot be the first queue in a pipeline")

@@ -31,10 +31,10 @@ from skyplane_b200.operators import GatewayCompressHash
 def _drain_status(store: ChunkStore, acc: Dict):
     try:
         while True:
-            rec = store.chunk_status_queue.get_nowait()
-            acc["states"][rec["state"]] = acc["states"].get(rec["state"], 0) + 1
-            acc["comp"] += rec.get("compressed_size_bytes", 0)
-            acc["raw"] += rec.get("uncompressed_size_bytes", 0)
+            for rec in store.iter_status_records(store.chunk_status_queue.get_nowait()):
+                acc["states"][rec["state"]] = acc["states"].get(rec["state"], 0) + 1
+                acc["comp"] += rec.get("compressed_size_bytes", 0)
+                acc["raw"] += rec.get("uncompressed_size_bytes", 0)
     except queue.Empty:
         pass
 
@@ -83,7 +83,8 @@ def run_stream(
                 raise RuntimeError("operator failed:\n" + err_q.get(timeout=5))
             if time.time() > deadline:
                 raise TimeoutError(f"harness timed out with {done}/{n_requests} chunks done")
-            while sent < n_requests and sent - done < window:
+            fresh = []
+            while sent < n_requests and sent - done < window and len(fresh) < 256:
                 k = sent % len(pool_files)
                 cid = uuid.uuid4().hex
                 dst = store.get_chunk_file_path(cid)
@@ -95,32 +96,33 @@ def run_stream(
                 req = ChunkRequest(Chunk(src_key=f"obj/{k}", dest_key=f"obj/{k}", chunk_id=cid, chunk_length_bytes=pool_lens[k], partition_id="0"))
                 if t0 is None and warmup_requests == 0:
                     t0 = time.perf_counter()
-                store.add_chunk_request(req)
+                fresh.append(req)
                 sent += 1
+            store.add_chunk_requests(fresh)  # (what the gateway API does per POST of a chunk-request list)
             _drain_status(store, status_acc)
-            try:
-                r = qout.get_nowait()
-            except queue.Empty:
+            finished = qout.get_batch_nowait(1024)
+            if not finished:
                 time.sleep(0.0005)
                 continue
-            done += 1
-            if done <= warmup_requests:
-                if done == warmup_requests:
-                    t0 = time.perf_counter()
-            else:
-                total_bytes += r.chunk.chunk_length_bytes
-            cid = r.chunk.chunk_id
-            rec = {
-                "chunk_id": cid,
-                "pool_index": pool_of.pop(cid),
-                "md5": r.chunk.md5_hash.hex() if r.chunk.md5_hash else None,
-                "raw_len": r.chunk.chunk_length_bytes,
-                "frame_path": str(store.get_compressed_file_path(cid)) if keep_frames else None,
-            }
-            records.append(rec)
-            if on_done is not None:
-                on_done(r)
-            store.get_chunk_file_path(cid).unlink(missing_ok=True)  # what the API thread does after the terminal op
+            for r in finished:
+                done += 1
+                if done <= warmup_requests:
+                    if done == warmup_requests:
+                        t0 = time.perf_counter()
+                else:
+                    total_bytes += r.chunk.chunk_length_bytes
+                cid = r.chunk.chunk_id
+                rec = {
+                    "chunk_id": cid,
+                    "pool_index": pool_of.pop(cid),
+                    "md5": r.chunk.md5_hash.hex() if r.chunk.md5_hash else None,
+                    "raw_len": r.chunk.chunk_length_bytes,
+                    "frame_path": str(store.get_compressed_file_path(cid)) if keep_frames else None,
+                }
+                records.append(rec)
+                if on_done is not None:
+                    on_done(r)
+                store.get_chunk_file_path(cid).unlink(missing_ok=True)  # what the API thread does after the terminal op
         wall = time.perf_counter() - t0 if t0 is not None else 0.0
     finally:
         # children flush their status records while exiting: keep draining or join() would block on a full pipe

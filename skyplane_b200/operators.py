@@ -318,6 +318,13 @@ class GatewayCompressHash(GatewayOperator):
         if self.output_queue is not None:
             self.output_queue.put(r)
 
+    def _complete_many(self, worker_id: int, reqs: List[ChunkRequest]):
+        """`complete` records and the hand-over to the next operator for a whole batch: one queue element each."""
+        metas = [r.__dict__.pop("_stage_meta", None) for r in reqs]
+        self.chunk_store.log_chunk_states(reqs, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id, metadata=metas)
+        if self.output_queue is not None:
+            self.output_queue.put_many(reqs)
+
     def worker_loop(self, worker_id: int, *args):
         """Batch-draining, double-buffered loop with the reference's logging / error conventions: while the GPU
         works on one batch the next one is read from the chunk files into the other staging slot."""
@@ -333,8 +340,8 @@ class GatewayCompressHash(GatewayOperator):
                     if stage_free:
                         room = self.max_batch_chunks - len(backlog)
                         fresh = self.input_queue.get_batch_nowait(room, self.handle) if room > 0 else []
-                        for r in fresh:
-                            self.chunk_store.log_chunk_state(r, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
+                        if fresh:
+                            self.chunk_store.log_chunk_states(fresh, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
                         cand = backlog + fresh
                         if cand:
                             slot, launched, not_ready, leftover = self._launch(cand)
@@ -350,8 +357,7 @@ class GatewayCompressHash(GatewayOperator):
                     if inflight:
                         slot, reqs = inflight.pop(0)
                         self._finish(slot, reqs)
-                        for r in reqs:
-                            self._complete(worker_id, r)
+                        self._complete_many(worker_id, reqs)
                     elif not backlog:
                         time.sleep(0.0005)
                 except Exception as e:
@@ -360,8 +366,7 @@ class GatewayCompressHash(GatewayOperator):
             if not self.error_event.is_set():
                 for slot, reqs in inflight:
                     self._finish(slot, reqs)
-                    for r in reqs:
-                        self._complete(worker_id, r)
+                    self._complete_many(worker_id, reqs)
         finally:
             self.worker_exit(worker_id)
 
@@ -477,14 +482,13 @@ class GatewayDecompressVerify(GatewayOperator):
                     if not reqs:
                         time.sleep(0.001)
                         continue
-                    for r in reqs:
-                        self.chunk_store.log_chunk_state(r, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
+                    self.chunk_store.log_chunk_states(reqs, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
                     done = self.process_batch(reqs)
-                    for r, good in zip(reqs, done):
-                        if good:
-                            self.chunk_store.log_chunk_state(r, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id)
-                            if self.output_queue is not None:
-                                self.output_queue.put(r)
+                    good = [r for r, g in zip(reqs, done) if g]
+                    if good:
+                        self.chunk_store.log_chunk_states(good, ChunkState.complete, operator_handle=self.handle, worker_id=worker_id)
+                        if self.output_queue is not None:
+                            self.output_queue.put_many(good)
                     retry = [r for r, good in zip(reqs, done) if not good]
                     if retry:
                         if len(retry) == len(reqs):

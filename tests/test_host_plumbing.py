@@ -409,7 +409,7 @@ def test_compress_hash_worker_loop_with_stub_stage(tmp_path):
         t0 = time.time()
         while time.time() - t0 < 5 and sum(1 for x in recs if x["state"] == "complete") < len(datas):
             try:
-                recs.append(cs.chunk_status_queue.get(timeout=0.2))
+                recs.extend(cs.iter_status_records(cs.chunk_status_queue.get(timeout=0.2)))
             except queue.Empty:
                 pass
         done = [x for x in recs if x["state"] == "complete"]
@@ -733,11 +733,12 @@ def test_local_operators_pipeline_from_program_json(tmp_path):
         t0 = time.time()
         while len(done) < len(ids) and time.time() - t0 < 30 and not ev.is_set():
             try:
-                rec = cs.chunk_status_queue.get(timeout=0.2)
+                item = cs.chunk_status_queue.get(timeout=0.2)
             except queue.Empty:
                 continue
-            if rec["handle"] == "write_local_w" and rec["state"] == "complete":
-                done.add(rec["chunk_id"])
+            for rec in cs.iter_status_records(item):  # the batched operator ships its records as lists
+                if rec["handle"] == "write_local_w" and rec["state"] == "complete":
+                    done.add(rec["chunk_id"])
         assert done == set(ids) and not ev.is_set()
         for cid in ids:
             data = cs.get_chunk_file_path(cid).read_bytes()

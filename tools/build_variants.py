@@ -8,10 +8,9 @@ sys.path.insert(0, str(ROOT))
 from skyplane_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "p10_e4096": {"SKY_PARSERS": 10, "SKY_LZ4_ENTRIES": 4096},
-    "p8_e4096": {"SKY_PARSERS": 8, "SKY_LZ4_ENTRIES": 4096},
-    "p6_e4096": {"SKY_PARSERS": 6, "SKY_LZ4_ENTRIES": 4096},
-    "p12_e3072": {"SKY_PARSERS": 12, "SKY_LZ4_ENTRIES": 3072},
+    "pr2_pa10": {"SKY_PROBERS": 2, "SKY_PARSERS": 10},
+    "pr3_pa9": {"SKY_PROBERS": 3, "SKY_PARSERS": 9},
+    "pr4_pa8": {"SKY_PROBERS": 4, "SKY_PARSERS": 8},
 }
 
 if __name__ == "__main__":
