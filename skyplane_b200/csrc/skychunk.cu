@@ -48,11 +48,7 @@ namespace sky {
 #define SKY_PARSERS 10
 #endif
 constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
-#ifndef SKY_PROBERS
-#define SKY_PROBERS 2
-#endif
-constexpr int kProbers = SKY_PROBERS;     // prober warps (0..): they take the 256-slot batches round-robin
-static_assert(kProbers >= 1 && kProbers <= 4, "SKY_PROBERS must be 1..4");
+constexpr int kProbers = 2;               // prober warps (0 and 1): they take alternate 256-slot batches
 constexpr int kWarps = kProbers + kParsers;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRing = kParsers + 3;       // segment slots between the prober and the parsers
@@ -139,24 +135,6 @@ template <int kId>
 __device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, 64;" ::"n"(kId) : "memory"); }
 template <int kId>
 __device__ __forceinline__ void bar_wait() { asm volatile("bar.sync %0, 64;" ::"n"(kId) : "memory"); }
-// token from prober i to prober (i + 1) % kProbers travels on barrier 1 + i (one arriving warp + one waiting warp)
-__device__ __forceinline__ void token_pass(unsigned i) {
-    switch (i) {
-    case 0: bar_arrive<1>(); break;
-    case 1: bar_arrive<2>(); break;
-    case 2: bar_arrive<3>(); break;
-    default: bar_arrive<4>(); break;
-    }
-}
-__device__ __forceinline__ void token_wait(unsigned i) {
-    switch ((i + kProbers - 1) % kProbers) {
-    case 0: bar_wait<1>(); break;
-    case 1: bar_wait<2>(); break;
-    case 2: bar_wait<3>(); break;
-    default: bar_wait<4>(); break;
-    }
-}
-__device__ __forceinline__ void probers_sync() { asm volatile("bar.sync 5, %0;" ::"n"(kProbers * 32) : "memory"); }
 __device__ __forceinline__ uint32_t ld_relaxed32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -270,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     const bool pace = do_md5 && !(p.flags & SKY_F_NO_PACING);
     uint8_t *scratch = p.scratch + (size_t)blockIdx.x * kScratchBytes;
     uint32_t gseq = 0;        // probers: sequence number of the next segment they publish (runs across blocks)
-    uint32_t gbatch = 0;      // probers: running batch number (its owner is gbatch % kProbers)
+    uint32_t batches_done = 0;  // prober 0: nothing to wait for before the kernel's very first batch
     uint32_t my_seq = 0;      // parser: the sequence number it holds a claim on
     bool have_claim = false;
     uint32_t in_phase = 0;
@@ -287,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
         const uint32_t L = dsc->L;
 
         if (warp < kProbers) {
-            // ---------------------------------------------------------------- probers (warps 0..kProbers-1, batches round-robin)
+            // ---------------------------------------------------------------- probers (warps 0 and 1, alternate batches)
             if (warp == 0) {
                 if (lane == 0) {
                     const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
@@ -296,13 +274,14 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                     for (uint32_t o = 0; o < bytes; o += kLoadPiece)  // several copies in flight: the pieces stream in parallel
                         bulk_load(in + o, src + o, min(kLoadPiece, bytes - o), &ctl->in_full);
                 }
-                // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty"
+                // clear the table meanwhile: entry 0 = (position 0, tag 0) doubles as "empty".  (Warp 1's first table access
+                // follows warp 0's first table phase through the token, so it sees the cleared table.)
                 uint4 *t4 = reinterpret_cast<uint4 *>(tab);
                 const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
                 for (uint32_t k = lane; k < kEntries / 4; k += 32) t4[k] = z;
+                __syncwarp();
             }
-            probers_sync();  // the table is clear before any prober's table phase
             mbar_wait(&ctl->in_full, in_phase);
             in_phase ^= 1;
             uint32_t nseg = 0;
@@ -317,14 +296,18 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                     const uint32_t si = gseq % kRing, ph = (gseq / kRing) & 1u;
                     SegSlot *slot = ring + si;
 #pragma unroll 1
-                    for (uint32_t b = 0; b < 4; b++, gbatch++) {
-                        if (gbatch % kProbers != warp) continue;  // batches go round the probers
+                    for (uint32_t b = warp; b < 4; b += kProbers) {
                         const uint32_t hits = probe_batch(smem_u32(in), smem_u32(tab), smem_u32(slot->offs), smem_u32(slot->masks), seg_pos, slog, b,
                                                           mflimit, lane, [&]() {
-                            // my turn at the table: the previous batch's owner has finished its table phase
-                            if (gbatch) token_wait(warp);
-                            if (b == 0) mbar_wait(&ctl->empty[si], ph ^ 1u);  // the ring slot is free again
+                            // my turn at the table: the other prober has finished the previous batch
+                            if (warp == 0) {
+                                if (batches_done) bar_wait<2>();
+                                if (b == 0) mbar_wait(&ctl->empty[si], ph ^ 1u);  // the ring slot is free again
+                            } else {
+                                bar_wait<1>();
+                            }
                         });
+                        batches_done = 1;
                         if (lane == 0) {
                             ctl->seg_hit[nseg & 3u] = (b == 0 ? 0u : ctl->seg_hit[nseg & 3u]) | hits;
                             if (b == 0) {
@@ -334,17 +317,16 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                             }
                         }
                         __syncwarp();
-                        if (b == 3 && lane == 0) mbar_arrive(&ctl->full[si]);  // (release: every prober's slot writes are ordered before it)
+                        if (b == 3 && lane == 0) mbar_arrive(&ctl->full[si]);  // (release: both probers' slot writes are ordered before it)
                         __threadfence_block();
-                        token_pass(warp);
+                        if (warp == 0) bar_arrive<1>(); else bar_arrive<2>();  // pass the token
                     }
                     seg_pos += kSegSlots << slog;
                     gseq++;
                     nseg++;
                 }
             }
-            probers_sync();  // the last batch is done, whoever owned it
-            if (warp == 0 && lane == 0) {
+            if (warp == kProbers - 1 && lane == 0) {
                 ctl->nseg = nseg;
                 __threadfence_block();
                 ctl->block_end_seq = gseq;

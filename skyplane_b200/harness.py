@@ -54,6 +54,7 @@ def run_stream(
     on_done: Optional[Callable[[ChunkRequest], None]] = None,
     warmup_requests: int = 0,
     operator_cls=GatewayCompressHash,
+    n_slots: int = 3,
 ) -> Dict:
     """Stream ``n_requests`` chunk requests (recycling ``pool_files`` by hard link) through the operator.
 
@@ -67,7 +68,7 @@ def run_stream(
     err_ev, err_q = mp.Event(), mp.Queue()
     op = operator_cls(
         "compress_hash", "local:box", qin, qout, err_ev, err_q, store, n_processes=n_workers,
-        max_batch_chunks=max_batch_chunks, max_batch_bytes=max_batch_bytes, n_gpus=n_gpus, keep_frames_on_disk=keep_frames,
+        max_batch_chunks=max_batch_chunks, max_batch_bytes=max_batch_bytes, n_gpus=n_gpus, keep_frames_on_disk=keep_frames, n_slots=n_slots,
     )
     op.start_workers()
     records: List[Dict] = []
@@ -151,7 +152,8 @@ def main():
     ap.add_argument("--chunk-mib", type=float, default=8)
     ap.add_argument("--pool", type=int, default=32)
     ap.add_argument("--workload", choices=["random", "silesia", "mixed"], default="mixed")
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=128, help="chunks per kernel launch")
+    ap.add_argument("--slots", type=int, default=3, help="launches in flight per worker")
     ap.add_argument("--warmup", type=int, default=-1, help="untimed leading requests (default: 4 batches per GPU)")
     ap.add_argument("--dir", default=None)
     a = ap.parse_args()
@@ -173,9 +175,9 @@ def main():
         lens.append(n)
         digests.append(hashlib.md5(data).hexdigest())  # hashlib = the reference's own call (s3_interface.py:181)
     try:
-        warm = a.warmup if a.warmup >= 0 else 4 * a.batch * a.gpus
+        warm = a.warmup if a.warmup >= 0 else (a.slots + 1) * a.batch * a.gpus
         res = run_stream(base / "chunks", files, lens, a.chunks + warm, n_workers=a.gpus, n_gpus=a.gpus, max_batch_chunks=a.batch,
-                         max_batch_bytes=max(n * a.batch, 64 << 20), keep_frames=False, window=max(256, 4 * a.batch * a.gpus),
+                         max_batch_bytes=max(n * a.batch, 64 << 20), keep_frames=False, window=max(256, (a.slots + 2) * a.batch * a.gpus), n_slots=a.slots,
                          warmup_requests=warm)
         bad = [r["chunk_id"] for r in res["records"] if r["md5"] != digests[r["pool_index"]]]
         if bad:

@@ -132,6 +132,7 @@ class GatewayCompressHash(GatewayOperator):
         ingest_read_local: bool = True,
         e2ee_key_bytes: Optional[bytes] = None,
         sink=None,
+        n_slots: int = 3,
     ):
         """use_compression / e2ee_key_bytes: GatewaySender's arguments of the same name (gateway_operator.py:154-168):
         ``use_compression=False`` digests the chunk and lets it pass through uncompressed (``is_compressed=False``);
@@ -143,6 +144,9 @@ class GatewayCompressHash(GatewayOperator):
         self.use_compression = True if use_compression is None else bool(use_compression)
         self.e2ee_key_bytes = e2ee_key_bytes
         self.sink = sink
+        # batches in flight per worker: a batch of 8 MiB chunks spends >= 70 ms on the GPU whatever its size (one serial MD5
+        # chain per chunk), so throughput = chunks in flight / 70 ms -- keep several batches going
+        self.n_slots = max(2, n_slots)
         self._sock = None
         self.max_batch_chunks = max_batch_chunks
         self.max_batch_bytes = max_batch_bytes
@@ -167,7 +171,7 @@ class GatewayCompressHash(GatewayOperator):
                 from skyplane_b200.numa import bind_to_gpu
 
                 bind_to_gpu(device)  # pinned staging buffers on the GPU's own socket
-            self._stage = ChunkStage(device, self.max_batch_bytes, self.max_batch_chunks, n_slots=2)
+            self._stage = ChunkStage(device, self.max_batch_bytes, self.max_batch_chunks, n_slots=self.n_slots)
             if self.e2ee_key_bytes is not None:
                 self._stage.set_e2ee_key(self.e2ee_key_bytes)
         return self._stage
@@ -352,7 +356,7 @@ class GatewayCompressHash(GatewayOperator):
                                 time.sleep(0.1 if slot is None and not inflight else 0)
                                 for k in not_ready:
                                     self.input_queue.put(cand[k])
-                            if slot is not None and len(inflight) < 2:
+                            if slot is not None and len(inflight) < self.n_slots:
                                 continue  # try to get a second batch going before blocking on the first
                     if inflight:
                         slot, reqs = inflight.pop(0)
