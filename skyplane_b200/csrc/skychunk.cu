@@ -51,7 +51,10 @@ constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
 constexpr int kProbers = 2;               // prober warps (0 and 1): they take alternate 256-slot batches
 constexpr int kWarps = kProbers + kParsers;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRing = kParsers + 3;       // segment slots between the prober and the parsers
+#ifndef SKY_RING_EXTRA
+#define SKY_RING_EXTRA 3
+#endif
+constexpr int kRing = kParsers + SKY_RING_EXTRA;       // segment slots between the prober and the parsers
 constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
 constexpr uint32_t kLoadPiece = 8192;     // bytes per bulk copy of the block load
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
             if (warp == kProbers - 1 && lane == 0) {
                 ctl->nseg = nseg;
                 __threadfence_block();
-                ctl->block_end_seq = gseq;
+                atomicExch(const_cast<uint32_t *>(&ctl->block_end_seq), gseq);  // (atomic: the parsers poll this word)
             }
         } else {
             // ---------------------------------------------------------------- parsers
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 const uint32_t si = my_seq % kRing, ph = (my_seq / kRing) & 1u;
                 bool got = true;
                 while (!mbar_try_wait_hint(&ctl->full[si], ph, 1000u)) {
-                    if (ctl->block_end_seq <= my_seq) {  // this block has no such segment: keep the claim for the next block
+                    if (atomicAdd(const_cast<uint32_t *>(&ctl->block_end_seq), 0u) <= my_seq) {  // no such segment in this block: keep the claim
                         got = mbar_try_wait(&ctl->full[si], ph);
                         break;
                     }

@@ -8,9 +8,10 @@ sys.path.insert(0, str(ROOT))
 from skyplane_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "pr2_pa10": {"SKY_PROBERS": 2, "SKY_PARSERS": 10},
-    "pr3_pa9": {"SKY_PROBERS": 3, "SKY_PARSERS": 9},
-    "pr4_pa8": {"SKY_PROBERS": 4, "SKY_PARSERS": 8},
+    "pa10": {"SKY_PARSERS": 10},
+    "pa11_r2": {"SKY_PARSERS": 11, "SKY_RING_EXTRA": 2},
+    "pa10_lit32": {"SKY_PARSERS": 10, "SKY_COOP_LIT": 32},
+    "pa10_lit8": {"SKY_PARSERS": 10, "SKY_COOP_LIT": 8},
 }
 
 if __name__ == "__main__":
