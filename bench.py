@@ -267,12 +267,11 @@ def run_reference(args):
     value = n * chunk_bytes * args.steps / total / 1e9
     per_step = sorted(n * chunk_bytes / x / 1e9 for x in t)
     single = ref.single_core_gbs()
-    cfg = workload_config(args, world)
-    cfg["compression_ratio"] = ref.last_ratio
+    cfg = workload_config(args, world)  # identical to the GPU arm's `config`: both arms name the workload, nothing else
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
-        "data": "synthetic", "config": cfg,
+        "data": "synthetic", "config": cfg, "details": {"compression_ratio": ref.last_ratio},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "single_core_gbs": single,
                          "effective_parallelism": value / single if single else None, "per_core_gbs": value / ref.cores,
                          "step_gbs_min_median_max": [per_step[0], per_step[len(per_step) // 2], per_step[-1]], "host": host_facts(),
@@ -599,11 +598,11 @@ def run_gpu(args):
 
     if rank == 0:
         cfg = workload_config(args, world)
-        cfg.update({"compression_ratio": ratio, "numa_node_rank0": numa_node, "kernel_build": native.kernel_config()})
+        details = {"compression_ratio": ratio, "numa_node_rank0": numa_node, "kernel_build": native.kernel_config()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/u32", "data": "synthetic", "config": cfg,
+            "dtype": "u8/u32", "data": "synthetic", "config": cfg, "details": details,
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "config3": config3, "queue_e2e": queue_e2e,
         }

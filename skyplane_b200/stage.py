@@ -120,6 +120,31 @@ class ChunkStage:
             raise AssertionError(f"chunk file {path} has size != {length}")
         return len(slot.lens) - 1
 
+    def add_stream(self, slot: _Slot, body, length: int) -> int:
+        """Ingest without a chunk file: fill the next staging range straight from a streaming
+        body -- any object with ``readinto(buffer)`` (a file, a socket file, ``io.BufferedReader`` around an HTTP response,
+        botocore's ``StreamingBody._raw_stream``) or ``read(n)`` -- the way ``download_object`` loops over 64 KiB pieces
+        (skyplane/obj_store/s3_interface.py:183-191), minus the tmpfs file and minus the host-side MD5 (the GPU supplies it)."""
+        dst = slot.reserve(length)
+        got = 0
+        readinto = getattr(body, "readinto", None)
+        while got < length:
+            if readinto is not None:
+                r = readinto(dst[got:])
+            else:
+                piece = body.read(min(length - got, 1 << 20))
+                r = len(piece)
+                dst[got : got + r] = piece
+            if not r:
+                break
+            got += r
+        if got != length:
+            slot.in_off.pop(); slot.lens.pop(); slot.out_off.pop()
+            slot.in_used -= native.round16(length)
+            slot.out_used -= native.round16(native.frame_bound(length) + native.BOX_OVERHEAD)
+            raise EOFError(f"stream ended after {got} of {length} bytes")
+        return len(slot.lens) - 1
+
     def set_e2ee_key(self, key: Optional[bytes]):
         """SecretBox key (32 bytes) for encrypt=True batches / decode(encrypted=True); None switches E2EE off."""
         self.ctx.set_e2ee_key(key)

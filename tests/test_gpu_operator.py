@@ -65,3 +65,69 @@ def test_operator_in_queue_harness():
         import shutil
 
         shutil.rmtree(base, ignore_errors=True)
+
+
+def test_ingest_without_chunk_files():
+    """SURVEY section 8f row 3 on the GPU: (a) `read_local` requests are byte ranges of one source object, read straight
+    into the staging slot by the operator (no <chunk_id>.chunk); (b) a streaming body (readinto / read) fills a slot through
+    ChunkStage.add_stream.  Digests equal hashlib's over exactly the requested range (s3_interface.py:178-194)."""
+    import io
+    import multiprocessing as mp
+
+    from skyplane_b200.chunk import Chunk, ChunkRequest
+    from skyplane_b200.chunk_store import ChunkStore
+    from skyplane_b200.gateway_queue import GatewayQueue
+    from skyplane_b200.operators import GatewayCompressHash
+    from skyplane_b200.stage import ChunkStage
+
+    base = Path(tempfile.mkdtemp(prefix="skyb200_ingest_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None))
+    try:
+        obj = synth.silesia_like_chunk(7, 5 << 20) + synth.random_chunk(8, (3 << 20) + 1234)
+        src = base / "object.bin"
+        src.write_bytes(obj)
+        cs = ChunkStore(base / "chunks")
+        qin, qout = GatewayQueue(), GatewayQueue()
+        err_ev, err_q = mp.Event(), mp.Queue()
+        op = GatewayCompressHash("ch", "test:r", qin, qout, err_ev, err_q, cs, n_processes=1, max_batch_chunks=8, max_batch_bytes=32 << 20)
+        ranges = [(0, 1 << 20), (1 << 20, (2 << 20) + 77), ((3 << 20) + 77, len(obj) - (3 << 20) - 77), (12345, 1), (len(obj) - 13, 13)]
+        # (the plugin method is called in-process: this pytest process already owns a CUDA context, so it must not fork)
+        op.worker_id = 0
+        try:
+            reqs = [ChunkRequest(Chunk(str(src), "dst", "%032x" % (0xFEED00 + i), n, partition_id="0", file_offset_bytes=off), src_type="read_local")
+                    for i, (off, n) in enumerate(ranges)]
+            assert op.process_batch(reqs) == [True] * len(reqs)
+            assert op.process(ChunkRequest(Chunk(str(src), "dst", "%032x" % 0xFEEDFF, 10, partition_id="0", file_offset_bytes=len(obj) - 5),
+                                           src_type="read_local")) is False  # range not (yet) inside the object: retry, not an error
+            for r, (off, n) in zip(reqs, ranges):
+                data = obj[off: off + n]
+                assert r.chunk.md5_hash == hashlib.md5(data).digest()
+                assert oracle.lz4f_decode(cs.get_compressed_file_path(r.chunk.chunk_id).read_bytes(), n) == data
+                assert not cs.get_chunk_file_path(r.chunk.chunk_id).exists()  # nothing was staged on tmpfs
+        finally:
+            op.worker_exit(0)
+        # (b) streaming bodies
+        stage = ChunkStage(0, max_batch_bytes=32 << 20, max_chunks=8, n_slots=1)
+        try:
+            class ReadOnly:  # a body without readinto, like botocore's StreamingBody
+                def __init__(self, b):
+                    self.f = io.BytesIO(b)
+
+                def read(self, n):
+                    return self.f.read(min(n, 70000))
+
+            slot = stage.begin()
+            stage.add_stream(slot, io.BytesIO(obj[: 3 << 20]), 3 << 20)
+            stage.add_stream(slot, ReadOnly(obj[3 << 20:]), len(obj) - (3 << 20))
+            with pytest.raises(EOFError):
+                stage.add_stream(slot, io.BytesIO(b"short"), 100)
+            stage.launch(slot)
+            a, b = stage.collect(slot)
+            assert a.md5 == hashlib.md5(obj[: 3 << 20]).digest() and b.md5 == hashlib.md5(obj[3 << 20:]).digest()
+            assert oracle.lz4f_decode(bytes(a.frame), 3 << 20) == obj[: 3 << 20]
+            assert oracle.lz4f_decode(bytes(b.frame), len(obj) - (3 << 20)) == obj[3 << 20:]
+        finally:
+            stage.close()
+    finally:
+        import shutil
+
+        shutil.rmtree(base, ignore_errors=True)
