@@ -230,8 +230,9 @@ __device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const ui
 // CTA-per-block compressor.  One CTA owns one 64 KiB block at a time:
 //   * the block is brought into shared memory with ONE bulk async copy (TMA 1-D, cp.async.bulk + mbarrier);
 //   * warp 0 (the prober) walks the block segment by segment (kSegSlots probe slots each): hash 5 bytes, ONE
-//     shared-memory lookup of (pos16 | tag16) per slot, no byte of the candidate is read; lanes of a 32-slot group that
-//     hash alike are ordered with one match.any so the result equals sequential insertion.  Per segment it publishes a
+//     shared-memory lookup of (pos16 | tag16) per slot, no byte of the candidate is read; the 32 slots of a group look the
+//     table up together and then replace their entries (atomic max: the last slot stays); short periods inside a group
+//     are caught by comparing hashes 3, 4 and 8 lanes apart.  Per segment it publishes a
 //     hit bit mask and the candidate offsets through a ring of shared-memory slots (mbarrier full / empty pairs);
 //   * the parser warps each take whole segments from the ring and parse them INDEPENDENTLY (cursor and anchor start at the
 //     segment start, matches are clipped to the segment end): per accepted match one warp-wide round compares 23 bytes
@@ -430,68 +431,83 @@ __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t 
 }
 
 // ---- prober: one batch of 8 groups (256 probe slots) of a segment.
-// Phase A -- everything that does not depend on the table: input words, hash, the match.any ordering of the lanes (which
-// lane is the most recent earlier occurrence inside the group, which lane stores) -- for all 8 groups.  match.any takes time
-// in proportion to the number of distinct values (32 rounds when all lanes differ, the common case), so the CTA runs TWO
-// prober warps that take alternate batches: one warp's phase A overlaps the other's table phase.
+// Phase A -- everything that does not depend on the table, for all 8 groups: input words, the 5-byte hash, the table index,
+// the entry this slot will leave behind (pos16 << 16 | tag16), and the in-group candidates: a lane whose 32-bit hash equals
+// that of the lane 3, 4 or 8 places below it takes that lane's slot as its candidate (three shuffles; periods 1, 2, 3, 4
+// and 8 -- runs, UTF-16, pixels, words, doubles -- which the table cannot know yet because a group looks the table up before
+// any of its slots is inserted).  Nothing here orders the lanes by hash: round 2's first formulation used match.any for
+// that, and at 58 cycles of the SM's one ADU pipe per instruction it was what bounded the kernel (profiles/README.md).
 // `turn()` is called between the phases: it returns when the other prober has finished the previous batch's table phase.
-// Phase B -- the 8 table lookups and stores back to back (the LSU keeps a warp's shared-memory accesses in order, so group
-// k+1's lookup sees group k's store without waiting for group k's lookup to return).  Phase C -- consume the lookups:
-// hit masks and candidate offsets into the segment's ring slot.  Returns the OR of the batch's hit masks.
+// Phase B -- the 8 table lookups and updates back to back: every lane reads its entry, then every lane max-es its own in
+// (position in the high half: of the lanes that share an index the highest one stays, exactly what inserting the slots in
+// order leaves behind).  The LSU keeps a warp's shared-memory accesses in order, so group k+1's lookup sees group k's
+// update without waiting for group k's lookup to return.  Phase C -- consume the lookups: hit masks and candidate offsets
+// into the segment's ring slot.  Returns the OR of the batch's hit masks.
 // Slots past the last probe position (p > mflimit, only at the very end of a block, always the highest lanes) hash a
-// clamped position and are masked out of the hits; they may win a table store, which no later lookup can observe.
-__device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (0xffffffff for 0): one FLO
-    uint32_t r;
-    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
-    return r;
+// clamped position: the entries they leave in the table no later lookup can observe, and the hits they report the parser
+// masks out (parse_segment), so the prober spends nothing on them.
+// n = (the slot distance d << slog) << 16 if the lane d = 3, 4 or 8 places below has my hash (the nearest one), else unchanged
+__device__ __forceinline__ void near_slot(uint32_t &n, uint32_t hf, uint32_t c3, uint32_t c4, uint32_t c8) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b32 t;\n\t"
+        "shfl.sync.up.b32 t|p, %1, 8, 0, 0xffffffff;\n\t"
+        "setp.eq.and.u32 q, t, %1, p;\n\t"
+        "selp.u32 %0, %4, %0, q;\n\t"
+        "shfl.sync.up.b32 t|p, %1, 4, 0, 0xffffffff;\n\t"
+        "setp.eq.and.u32 q, t, %1, p;\n\t"
+        "selp.u32 %0, %3, %0, q;\n\t"
+        "shfl.sync.up.b32 t|p, %1, 3, 0, 0xffffffff;\n\t"
+        "setp.eq.and.u32 q, t, %1, p;\n\t"
+        "selp.u32 %0, %2, %0, q;\n\t"
+        "}"
+        : "+r"(n)
+        : "r"(hf), "r"(c3), "r"(c4), "r"(c8));
+}
+__device__ __forceinline__ void red_max_s(uint32_t a, uint32_t v) {
+    asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 template <class Turn>
 __device__ __forceinline__ uint32_t probe_batch(uint32_t in_s, uint32_t tab_s, uint32_t offs_s, uint32_t masks_s, uint32_t seg_pos,
                                                 uint32_t slog, uint32_t batch, uint32_t mflimit, unsigned lane, Turn turn) {
-    const unsigned lt_mask = (1u << lane) - 1u, gt_mask = ~((2u << lane) - 1u);
     const uint32_t pstep = 32u << slog;
     uint32_t p = seg_pos + ((batch * 256u + lane) << slog);
     // p & 3 is the same for every group of the segment (p advances by a multiple of 32): byte selectors are loop-invariant
     const uint32_t selv = 0x3210u + 0x1111u * (p & 3u), selb = 0x4440u | (p & 3u);
     const uint32_t offs_l = offs_s + (batch * 256u + lane) * 2u;
-    uint32_t idx[8], mine[8], e[8], e_near[8], anyhit = 0;
-    bool valid[8], has_lower[8], stores[8];
+    const uint32_t c3 = 0x30000u << slog, c4 = 0x40000u << slog, c8 = 0x80000u << slog;
+    uint32_t idx[8], mine[8], e[8], near[8], anyhit = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        valid[k] = p <= mflimit;
         const uint32_t pc = min(p, mflimit);
         const uint32_t a = in_s + (pc & ~3u);
         const uint32_t w0 = lds32(a), w1 = lds32(a + 4);
         uint32_t hf = __byte_perm(w0, w1, selv) * 2654435761u;
         hf = __byte_perm(w1, 0u, selb) * 0x85EBCA6Bu + hf;  // fifth byte
         idx[k] = __umulhi(hf, kEntries) * 4u;               // byte offset of the table entry
-        mine[k] = __byte_perm(p, hf, 0x6510);               // pos16 | hash bytes 1-2 as the tag
+        mine[k] = __byte_perm(p, hf, 0x1065);               // pos16 << 16 | hash bytes 1-2 as the tag
+        near[k] = 0u;
+        near_slot(near[k], hf, c3, c4, c8);
         p += pstep;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const unsigned grp = __match_any_sync(kFull, idx[k]);
-        const unsigned lower = grp & lt_mask;
-        has_lower[k] = lower != 0u;
-        e_near[k] = __shfl_sync(kFull, mine[k], bfind(lower));  // nearest lower lane = most recent occurrence (unused if none)
-        stores[k] = (grp & gt_mask) == 0u;                      // the highest lane of the group stores
     }
     turn();
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         e[k] = lds32(tab_s + idx[k]);
-        __syncwarp();  // (orders the lanes' table reads of this group before its writes)
-        if (stores[k]) sts32(tab_s + idx[k], mine[k]);
+        __syncwarp();  // (orders the lanes' table reads of this group before its updates)
+        red_max_s(tab_s + idx[k], mine[k]);
         __syncwarp();
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const uint32_t ek = has_lower[k] ? e_near[k] : e[k];  // a lower lane filled the slot more recently than the table knows
-        const uint32_t x = ek ^ mine[k];
-        const unsigned hits = __ballot_sync(kFull, valid[k] && (x - 1u) < 65535u);  // tag equal, position differs
+        uint32_t d = mine[k] - e[k];  // tags equal <=> low half 0 (then no borrow: the high half is the distance, >= 1 for
+        if (near[k]) d = near[k];     // a real entry, 0 only for slot 0 against the empty table)
+        const uint32_t off = d >> 16;
+        const unsigned hits = __ballot_sync(kFull, (d & 0xffffu) == 0u && off != 0u);
         anyhit |= hits;
         if (lane == 0) sts32(masks_s + (batch * 8u + (uint32_t)k) * 4u, hits);
-        sts16(offs_l + (uint32_t)k * 64u, mine[k] - ek);
+        sts16(offs_l + (uint32_t)k * 64u, off);
     }
     return anyhit;
 }
@@ -502,8 +518,10 @@ __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot
                                                 unsigned lane) {
     const uint32_t in32 = smem_u32(in), offs_s = smem_u32(slot->offs);
     const uint32_t seg_pos = slot->seg_pos, slog = slot->slog;
-    const uint32_t mymask = slot->masks[lane];
     const uint32_t mflimit = L - kMfLimit, matchlimit = L - kLastLiterals;
+    // group `lane` of the segment: only slots at positions <= mflimit were probed for real (the rest: block tail)
+    const uint32_t n_real = ((mflimit - seg_pos) >> slog) + 1u;  // (seg_pos <= mflimit for every segment)
+    const uint32_t mymask = slot->masks[lane] & ~__funnelshift_lc(0u, 0xffffffffu, min(max(n_real, lane * 32u) - lane * 32u, 32u));
     const uint32_t seg_lim = seg_pos + (kSegSlots << slog);
     const uint32_t mlim = min(matchlimit, seg_lim);                 // matches end at or before this
     const uint32_t seg_end = seg_lim > mflimit ? L : seg_lim;      // the last segment owns the block's tail

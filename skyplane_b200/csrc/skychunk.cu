@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     SegRec *recs = reinterpret_cast<SegRec *>(smem + kRecOff);
     SegPlan *plans = reinterpret_cast<SegPlan *>(smem + kPlanOff);
     Ctl *ctl = reinterpret_cast<Ctl *>(smem + kCtlOff);
+    uint32_t smem_s = smem_u32(smem);  // shared-window address of the CTA's buffer, kept in a register: left to itself the
+    asm volatile("" : "+r"(smem_s));   // compiler re-derives it (S2UR SR_CgaCtaId + ULEA) at the top of every prober batch
 
     const bool do_md5 = (p.flags & SKY_F_MD5) != 0, do_lz4 = (p.flags & SKY_F_LZ4) != 0;
     if (warp == 0 && lane == 0) {
@@ -300,8 +302,9 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                     SegSlot *slot = ring + si;
 #pragma unroll 1
                     for (uint32_t b = warp; b < 4; b += kProbers) {
-                        const uint32_t hits = probe_batch(smem_u32(in), smem_u32(tab), smem_u32(slot->offs), smem_u32(slot->masks), seg_pos, slog, b,
-                                                          mflimit, lane, [&]() {
+                        const uint32_t slot_s = smem_s + kRingOff + si * (uint32_t)sizeof(SegSlot);
+                        const uint32_t hits = probe_batch(smem_s + kInOff, smem_s + kTabOff, slot_s + (uint32_t)offsetof(SegSlot, offs),
+                                                          slot_s + (uint32_t)offsetof(SegSlot, masks), seg_pos, slog, b, mflimit, lane, [&]() {
                             // my turn at the table: the other prober has finished the previous batch
                             if (warp == 0) {
                                 if (batches_done) bar_wait<2>();

@@ -11,8 +11,11 @@
  *             slog starts at 0 for the first two segments; segment s+2's slog is 0 if segment s had any hit, else segment
  *             s+1's slog plus one (up to max_step_log) -- one segment of delay, so the kernel's two prober warps never
  *             wait for each other's verdict.
- *   probe   = every slot, in position order: hash 5 bytes, look the table entry (pos16 | tag16) up; hit = tag equal and
- *             entry older than the slot; the slot then replaces the entry.  No byte of the candidate is read here.
+ *   probe   = 32 slots (a group) at a time: hash 5 bytes, look the table entry (pos16 | tag16) up; hit = tag equal and
+ *             entry older than the slot.  A slot whose full 32-bit hash equals that of the slot 3, 4 or 8 places before it
+ *             in the same group takes that one as its candidate instead (short periods: pixels, words, doubles -- the
+ *             table cannot know them yet).  Then the group's slots replace their table entries, the last one staying.
+ *             No byte of the candidate is read here.
  *   parse   = per segment, independently of every other segment: cursor and anchor start at the segment start; walk the
  *             hits at or after the cursor; measure the real match length from byte 0 (this is also the verification),
  *             clipped to the segment end (and to the block's last-5-bytes rule); drop it if < 4; extend backwards by up
@@ -37,6 +40,10 @@ typedef struct {
     int max_step_log;  /* largest probe stride = 1 << this (kernel: 4) */
     int back_ext;      /* 1 = extend accepted matches backwards by up to 8 bytes (kernel: 1) */
     int clip;          /* 1 = matches end at the segment end (kernel: 1; 0 shows what the segment independence costs) */
+    int group_lag;     /* 1 = the 32 slots of a group all look the table up before any of them is inserted (kernel: 1);
+                          0 = every slot sees the slots before it (study variant: what a fully sequential probe would find) */
+    int near_mask;     /* with group_lag: bit d-1 set = a slot also compares its 5-byte hash with the slot d places before it
+                          in its group; the nearest equal one is its candidate, ahead of the table's (kernel: 0x8c = 3, 4, 8) */
 } tile_opts;
 
 static uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -53,6 +60,10 @@ static uint32_t emit(uint8_t *out, uint32_t op, const uint8_t *src, uint32_t anc
     return op;
 }
 
+static uint32_t hash5(const uint8_t *p) { return rd32(p) * 2654435761u + p[4] * 0x85EBCA6Bu; }  /* 5 bytes, two 32-bit multiplies */
+static uint32_t hidx(uint32_t hf, const tile_opts *o) { return (uint32_t)(((uint64_t)hf * (uint32_t)o->entries) >> 32); }
+static uint32_t htag(uint32_t hf) { return (hf >> 8) & 0xffffu; }  /* hash bytes 1-2: one PRMT in the kernel */
+
 typedef struct { uint64_t probes, hits, accepted, segments; } tile_stats;
 static tile_stats g_stats;
 void tile_model_stats(tile_stats *s, int reset) { *s = g_stats; if (reset) memset(&g_stats, 0, sizeof g_stats); }
@@ -64,24 +75,36 @@ uint32_t tile_compress_block(const uint8_t *src, uint32_t L, uint8_t *out, const
     uint16_t *off = malloc(2 * S);
     uint8_t *hit = malloc(S);
     uint32_t anchor = 0 /* start of the literals not yet emitted */, op = 0, result = 0;
+    uint32_t ghf[32];
     if (L >= MFLIMIT + 1) {
         const uint32_t mflimit = L - MFLIMIT, matchlimit = L - LASTLITERALS;
         uint32_t seg_pos = 0, slog = 0, slog_next = 0;  /* slog of this segment / of the next one */
         while (seg_pos <= mflimit) {
             g_stats.segments++;
-            /* ---- probe (sequential insertion; the kernel reproduces it 32 slots at a time with match.any) */
+            /* ---- probe, one group of 32 slots at a time */
             int anyhit = 0;
-            for (uint32_t i = 0; i < S; i++) {
-                const uint32_t p = seg_pos + (i << slog);
-                hit[i] = 0;
-                if (p > mflimit) continue;
-                const uint32_t hf = rd32(src + p) * 2654435761u + src[p + 4] * 0x85EBCA6Bu;  /* 5 bytes, two 32-bit multiplies */
-                const uint32_t idx = (uint32_t)(((uint64_t)hf * (uint32_t)o->entries) >> 32);
-                const uint32_t tag = (hf >> 8) & 0xffffu;  /* hash bytes 1-2: one PRMT in the kernel */
-                const uint32_t e = tab[idx], epos = e & 0xffffu;
-                g_stats.probes++;
-                if ((e >> 16) == tag && epos < p) { hit[i] = 1; off[i] = (uint16_t)(p - epos); anyhit = 1; g_stats.hits++; }
-                tab[idx] = p | (tag << 16);
+            for (uint32_t g = 0; g < S; g += 32) {
+                for (uint32_t i = g; i < g + 32; i++) {
+                    const uint32_t p = seg_pos + (i << slog);
+                    hit[i] = 0;
+                    ghf[i - g] = 0;
+                    if (p > mflimit) continue;
+                    const uint32_t hf = hash5(src + p);
+                    const uint32_t e = tab[hidx(hf, o)], epos = e & 0xffffu;
+                    ghf[i - g] = hf;
+                    g_stats.probes++;
+                    if ((e >> 16) == htag(hf) && epos < p) { hit[i] = 1; off[i] = (uint16_t)(p - epos); }
+                    if (o->group_lag) {  /* an equal hash 3, 4 or 8 slots back in the group is the nearer candidate */
+                        for (uint32_t d = 1; d <= i - g; d++)
+                            if ((((uint32_t)o->near_mask >> (d - 1)) & 1u) && ghf[i - g - d] == hf) { hit[i] = 1; off[i] = (uint16_t)(d << slog); break; }
+                    } else tab[hidx(hf, o)] = p | (htag(hf) << 16);
+                    if (hit[i]) { anyhit = 1; g_stats.hits++; }
+                }
+                if (o->group_lag)  /* the group's slots replace the table entries in slot order (the last one stays) */
+                    for (uint32_t i = g; i < g + 32; i++) {
+                        const uint32_t p = seg_pos + (i << slog);
+                        if (p <= mflimit) tab[hidx(ghf[i - g], o)] = p | (htag(ghf[i - g]) << 16);
+                    }
             }
             /* ---- parse: depends on nothing outside this segment */
             const uint32_t seg_lim = seg_pos + (S << slog);  /* first byte of the next segment */

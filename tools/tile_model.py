@@ -14,7 +14,7 @@ _lib = None
 
 class Opts(ctypes.Structure):
     _fields_ = [("entries", ctypes.c_int), ("seg_slots", ctypes.c_int), ("max_step_log", ctypes.c_int), ("back_ext", ctypes.c_int),
-                ("clip", ctypes.c_int)]
+                ("clip", ctypes.c_int), ("group_lag", ctypes.c_int), ("near_mask", ctypes.c_int)]
 
 
 class Stats(ctypes.Structure):
@@ -23,7 +23,7 @@ class Stats(ctypes.Structure):
 
 def kernel_opts(entries: int = 4096, seg_slots: int = 1024, max_step_log: int = 4) -> Opts:
     """The options the kernel in skyplane_b200/csrc/lz4.cuh implements."""
-    return Opts(entries, seg_slots, max_step_log, 1, 1)
+    return Opts(entries, seg_slots, max_step_log, 1, 1, 1, 0x8C)
 
 
 def lib():

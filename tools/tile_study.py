@@ -41,14 +41,19 @@ def liblz4_linked_size(data: bytes) -> int:
 
 
 VARIANTS = {
-    "kernel: 4096e seg1024 step16": tm.kernel_opts(),
-    "no segment clipping": Opts(4096, 1024, 4, 1, 0),
+    "kernel: 4096e seg1024 step16 near{3,4,8}": tm.kernel_opts(),
+    "no segment clipping": Opts(4096, 1024, 4, 1, 0, 1, 0x8C),
     "seg512": tm.kernel_opts(4096, 512),
     "seg2048": tm.kernel_opts(4096, 2048),
     "3072e": tm.kernel_opts(3072),
     "2048e": tm.kernel_opts(2048),
-    "no back ext": Opts(4096, 1024, 4, 0, 1),
+    "no back ext": Opts(4096, 1024, 4, 0, 1, 1, 0x8C),
     "step1": tm.kernel_opts(4096, 1024, 0),
+    "sequential probe (every slot sees the one before)": Opts(4096, 1024, 4, 1, 1, 0, 0),
+    "no in-group candidates": Opts(4096, 1024, 4, 1, 1, 1, 0),
+    "near {4}": Opts(4096, 1024, 4, 1, 1, 1, 0x8),
+    "near {1,2,3,4,8}": Opts(4096, 1024, 4, 1, 1, 1, 0x8F),
+    "near {1..31}": Opts(4096, 1024, 4, 1, 1, 1, 0x7FFFFFFF),
 }
 
 if __name__ == "__main__":
