@@ -446,6 +446,11 @@ __device__ __noinline__ uint32_t flush_seqs(uint8_t *__restrict__ out, uint32_t 
 // Slots past the last probe position (p > mflimit, only at the very end of a block, always the highest lanes) hash a
 // clamped position: the entries they leave in the table no later lookup can observe, and the hits they report the parser
 // masks out (parse_segment), so the prober spends nothing on them.
+__device__ __forceinline__ uint32_t bfind(uint32_t x) {  // index of the highest set bit (0xffffffff for 0): one FLO
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
 // n = (the slot distance d << slog) << 16 if the lane d = 3, 4 or 8 places below has my hash (the nearest one), else unchanged
 __device__ __forceinline__ void near_slot(uint32_t &n, uint32_t hf, uint32_t c3, uint32_t c4, uint32_t c8) {
     asm volatile(
@@ -545,7 +550,7 @@ __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot
             m &= __funnelshift_lc(0u, 0xffffffffu, (max(cur, gbase) - gbase + round_up) >> slog);  // slots the cursor has passed
             if (m == 0) continue;
         }
-        const uint32_t bit = (uint32_t)__ffs(m) - 1u;
+        const uint32_t bit = bfind(m & (0u - m));  // lowest set bit: two ALU ops + one FLO (ffs is BREV + FLO, both on the XU pipe)
         uint32_t pos = gbase + (bit << slog);
         const uint32_t off = lds16(offs_s + (sbase + bit) * 2u);
         const uint32_t cand = pos - off;
@@ -554,7 +559,7 @@ __device__ __forceinline__ SegRec parse_segment(const uint8_t *in, const SegSlot
         bool ok = false;
         if (jrel < (fwd_lane ? maxlen : room)) ok = lds8(in32 + pos + dl) == lds8(in32 + cand + dl);
         const unsigned z = ~__ballot_sync(kFull, ok) | 0x00800000u;  // bit 23 = stop bit of the forward scan
-        uint32_t mlen = (uint32_t)__ffs(z) - 1u;                   // 0..23
+        uint32_t mlen = bfind(z & (0u - z));                       // 0..23
         if (mlen - kMinMatch >= 23u - kMinMatch) {  // rare: a tag collision (< 4), or the match runs past the 23 bytes compared
             if (mlen < kMinMatch) {
                 m &= m - 1;
