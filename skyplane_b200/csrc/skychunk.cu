@@ -45,15 +45,23 @@
 namespace sky {
 
 #ifndef SKY_PARSERS
-#define SKY_PARSERS 10
+#define SKY_PARSERS 12
 #endif
 constexpr int kParsers = SKY_PARSERS;     // parser warps per CTA
 constexpr int kProbers = 2;               // prober warps (0 and 1): they take alternate 256-slot batches
 constexpr int kWarps = kProbers + kParsers;
 constexpr int kThreads = kWarps * 32;
 #ifndef SKY_RING_EXTRA
-#define SKY_RING_EXTRA 3
+#define SKY_RING_EXTRA 2
 #endif
+#ifndef SKY_WAIT_NS
+#define SKY_WAIT_NS 1024
+#endif
+#ifndef SKY_PACE_LEAD
+#define SKY_PACE_LEAD 0
+#endif
+constexpr uint32_t kWaitNs = SKY_WAIT_NS;       // longest sleep of a parser between two looks at its segment's barrier (0: hardware try_wait)
+constexpr uint32_t kPaceLead = SKY_PACE_LEAD;   // rows the compressor may run ahead of a chunk's MD5 lanes beyond the one they are in
 constexpr int kRing = kParsers + SKY_RING_EXTRA;       // segment slots between the prober and the parsers
 constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
@@ -176,7 +184,7 @@ __device__ __forceinline__ void claim_block(const Params &p, BlockDesc *d, bool 
             for (;;) {
                 const uint32_t pr = ld_relaxed32(pw);
                 // pr: 0 = digest not started, 0xffffffff = finished, else 1 + rows consumed (64-bit compare: no wrap)
-                if (pr == 0 || (uint64_t)j + 1 <= (uint64_t)pr + lead) break;
+                if (pr == 0 || (uint64_t)j + 1 <= (uint64_t)pr + lead + kPaceLead) break;
                 __nanosleep(ns);
                 if (ns < 4096) ns <<= 1;
             }
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
         const uint32_t L = dsc->L;
 
         if (warp < kProbers) {
-            // ---------------------------------------------------------------- probers (warps 0 and 1, alternate batches)
+            // ---------------------------------------------------------------- probers (warps 0 and 1, alternate batches of every segment)
             if (warp == 0) {
                 if (lane == 0) {
                     const uint32_t bytes = (L + 15u) & ~15u;  // (the input slab is readable up to the next multiple of 16)
@@ -350,10 +358,18 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 }
                 const uint32_t si = my_seq % kRing, ph = (my_seq / kRing) & 1u;
                 bool got = true;
-                while (!mbar_try_wait_hint(&ctl->full[si], ph, 1000u)) {
+                // Waiting for a segment must not cost issue slots: mbarrier.try_wait's hardware suspend ends at EVERY barrier
+                // event in the CTA (a few dozen ns apart here), which made the waiting loops a quarter of all instructions
+                // issued (profiles/README.md, r2_27).  Sleep with a doubling period instead.
+                unsigned ns = 32;
+                while (!(kWaitNs ? mbar_test_wait(&ctl->full[si], ph) : mbar_try_wait_hint(&ctl->full[si], ph, 1000u))) {
                     if (atomicAdd(const_cast<uint32_t *>(&ctl->block_end_seq), 0u) <= my_seq) {  // no such segment in this block: keep the claim
                         got = mbar_try_wait(&ctl->full[si], ph);
                         break;
+                    }
+                    if (kWaitNs) {
+                        __nanosleep(ns);
+                        if (ns < kWaitNs) ns <<= 1;
                     }
                 }
                 if (!got) break;
@@ -374,33 +390,77 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
         // ---------------------------------------------------------------- plan (warp 0)
         const uint32_t nseg = ctl->nseg;
         if (warp == 0) {
+            // String the segments together: the literals a segment leaves behind its last match (or a whole segment without
+            // a match) are carried into the next first sequence.  carry_out(s) = has_match(s) ? t(s) : carry_in(s) + t(s) is
+            // a scan of (reset, add) pairs: every lane folds its kPlanPerLane consecutive segments, the lanes are scanned with
+            // shuffles, then every lane replays its segments with the true carry and sizes them; a second scan places them.
+            constexpr uint32_t kPlanPerLane = (kMaxSegs + 31) / 32;
             uint32_t csize = 0;
-            if (lane == 0) {
-                uint32_t carry = 0, o = 0;
-                for (uint32_t s = 0; s < nseg; s++) {
-                    const SegRec r = recs[s];
-                    const uint32_t ml = r.lead_ml >> 16, t = r.off_t >> 16;
-                    SegPlan pl;
-                    pl.foff = o;
-                    pl.fll = 0;
-                    if (ml) {
-                        pl.fll = carry + (r.lead_ml & 0xffffu);
-                        o += seq_bytes_fast(pl.fll, ml);
-                        carry = t;
-                    } else {
-                        carry += t;
+            {
+                const uint32_t s0 = lane * kPlanPerLane;
+                uint32_t has = 0, val = 0;  // this lane's segments as one function of the incoming carry
+                for (uint32_t k = 0; k < kPlanPerLane; k++) {
+                    const uint32_t sg = s0 + k;
+                    if (sg < nseg) {
+                        const SegRec r = recs[sg];
+                        const uint32_t t = r.off_t >> 16;
+                        if (r.lead_ml >> 16) { has = 1; val = t; } else val += t;
                     }
-                    pl.moff = o;
-                    pl.pad = 0;
-                    o += r.mbytes;
-                    plans[s] = pl;
                 }
-                if (nseg == 0) carry = L;
-                ctl->last_lits = carry;
-                ctl->tail_off = o;  // where the final literal run starts (relative to the block's first data byte)
-                csize = o + 1 + carry + (carry >= 15 ? (carry - 15) / 255 + 1 : 0);
+                uint32_t ihas = has, ival = val;  // inclusive scan of the composition (earlier lanes first)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t ph_ = __shfl_up_sync(kFull, ihas, d), pv = __shfl_up_sync(kFull, ival, d);
+                    if ((int)lane >= d && !ihas) { ihas = ph_; ival += pv; }
+                }
+                uint32_t carry = __shfl_up_sync(kFull, ival, 1);  // what reaches this lane's first segment
+                if (lane == 0) carry = 0;
+                const uint32_t carry_end = __shfl_sync(kFull, ival, 31);  // literals behind the block's last match
+                uint32_t fll[kPlanPerLane], fsz[kPlanPerLane], msz[kPlanPerLane], mine_total = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < kPlanPerLane; k++) {
+                    const uint32_t sg = s0 + k;
+                    fll[k] = fsz[k] = msz[k] = 0;
+                    if (sg < nseg) {
+                        const SegRec r = recs[sg];
+                        const uint32_t ml = r.lead_ml >> 16, t = r.off_t >> 16;
+                        msz[k] = r.mbytes;
+                        if (ml) {
+                            fll[k] = carry + (r.lead_ml & 0xffffu);
+                            fsz[k] = seq_bytes_fast(fll[k], ml);
+                            carry = t;
+                        } else carry += t;
+                        mine_total += fsz[k] + msz[k];
+                    }
+                }
+                uint32_t incl = mine_total;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                    if ((int)lane >= d) incl += t;
+                }
+                uint32_t o = incl - mine_total;
+                const uint32_t total = __shfl_sync(kFull, incl, 31);
+#pragma unroll
+                for (uint32_t k = 0; k < kPlanPerLane; k++) {
+                    const uint32_t sg = s0 + k;
+                    if (sg < nseg) {
+                        SegPlan pl;
+                        pl.foff = o;
+                        pl.moff = o + fsz[k];
+                        pl.fll = fll[k];
+                        pl.pad = 0;
+                        plans[sg] = pl;
+                        o += fsz[k] + msz[k];
+                    }
+                }
+                const uint32_t last = nseg == 0 ? L : carry_end;
+                if (lane == 0) {
+                    ctl->last_lits = last;
+                    ctl->tail_off = total;  // where the final literal run starts (relative to the block's first data byte)
+                }
+                csize = total + 1 + last + (last >= 15 ? (last - 15) / 255 + 1 : 0);
             }
-            csize = __shfl_sync(kFull, csize, 0);
             const bool raw = csize > L - 1;  // LZ4F_makeBlock: a block that does not shrink is stored
             // OFF chain: learn where this block starts, tell the successor at once
             uint64_t st = 0;
