@@ -55,18 +55,21 @@ constexpr int kThreads = kWarps * 32;
 #define SKY_RING_EXTRA 2
 #endif
 #ifndef SKY_WAIT_NS
-#define SKY_WAIT_NS 1024
+#define SKY_WAIT_NS 0
 #endif
 #ifndef SKY_PACE_LEAD
 #define SKY_PACE_LEAD 0
 #endif
-constexpr uint32_t kWaitNs = SKY_WAIT_NS;       // longest sleep of a parser between two looks at its segment's barrier (0: hardware try_wait)
+constexpr uint32_t kWaitNs = SKY_WAIT_NS;       // 0: a waiting parser is parked by mbarrier.try_wait (measured best); else it sleeps, doubling up to this many ns
 constexpr uint32_t kPaceLead = SKY_PACE_LEAD;   // rows the compressor may run ahead of a chunk's MD5 lanes beyond the one they are in
 constexpr int kRing = kParsers + SKY_RING_EXTRA;       // segment slots between the prober and the parsers
 constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one per SM sub-partition), see sky_fused_kernel
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
 constexpr uint32_t kLoadPiece = 8192;     // bytes per bulk copy of the block load
 constexpr int kCtasPerSm = 2;             // fused kernel: 2 x ~110 KiB of shared memory per SM
+constexpr uint32_t kMaxSm = 512;          // %smid values the role table covers (B200: 148 SMs)
+constexpr uint32_t kCountersBytes = (16 + 2 * kMaxSm) * 4;
+constexpr uint32_t kRoleCompress = 1, kRoleDigest = 2;
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
 
@@ -82,6 +85,7 @@ struct Ctl {
     uint64_t full[kRing], empty[kRing];
     BlockDesc desc[2];              // by block-iteration parity
     uint32_t claim;                 // next segment sequence number a parser may take (runs across blocks)
+    uint32_t role;                  // kRoleDigest / kRoleCompress (decided per SM at kernel start)
     volatile uint32_t block_end_seq;  // sequence number after the current block's last segment (0xffffffff while probing)
     volatile uint32_t nseg;
     volatile uint32_t seg_hit[4];     // per segment (mod 4): OR of its batches' hit masks (decides the stride two segments on)
@@ -116,11 +120,12 @@ struct Params {
     uint32_t *md5_progress;     // per MD5 group: 0 = not started, else 1 + 64 KiB rows consumed (0xffffffff = done)
     uint64_t *out_len;          // per chunk frame length
     uint8_t *md5_out;           // 16 bytes per chunk
-    uint32_t *counters;         // [0] = LZ4 work counter
+    uint32_t *counters;         // [0] = LZ4 work counter, [1] = digest-SM tickets, [2] = MD5 group counter,
+                                // [16 + smid] = CTAs that reported from that SM, [16 + kMaxSm + smid] = the SM's role
     uint8_t *scratch;           // kScratchBytes per CTA: where a block's segments are compressed before its frame offset is known
     uint32_t n_chunks;
     uint32_t n_groups;
-    uint32_t n_md5_ctas;        // CTAs 0..n_md5_ctas-1 digest (4 groups each at a time) before they compress
+    uint32_t n_md5_sms;         // this many SMs digest (both of their CTAs, 4 MD5 warps each) before they compress
     uint32_t rows;  // max(1, max nblk)
     uint32_t flags;
 };
@@ -203,7 +208,7 @@ __device__ __forceinline__ void claim_block(const Params &p, BlockDesc *d, bool 
 }
 
 // Fused LZ4-frame + MD5 kernel.  Grid = 2 CTAs per SM, kWarps warps each.
-//   digest CTAs (blockIdx < n_md5_ctas): warps 0..3 each carry one MD5 group (32 chunks, lane = chunk, md5.cuh) at a time;
+//   digest CTAs (both CTAs of the first n_md5_sms SMs to report): warps 0..3 each carry one MD5 group (32 chunks, lane = chunk, md5.cuh) at a time;
 //       when the groups are done the CTA joins the compressors.
 //   compressor CTAs: one 64 KiB block at a time -- bulk-load it into shared memory, warp 0 probes, warps 1.. parse
 //       (lz4.cuh), warp 0 plans the block's layout and takes its frame offset from the OFF chain, all warps write it out.
@@ -234,9 +239,41 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     }
     __syncthreads();
 
-    if (do_md5 && blockIdx.x < p.n_md5_ctas) {
+    // Digest role per SM, not per CTA: an MD5 warp is a pure dependent chain (one instruction every ~5.4 cycles), so any
+    // compressor warp on its scheduler slows the chain, and a digest CTA's other warps cannot compress (its block buffer
+    // holds the MD5 rings).  The first n_md5_sms SMs to report therefore digest with BOTH their CTAs (8 MD5 warps, two per
+    // scheduler, nothing else on the SM); every other SM compresses from the start.  Groups are claimed dynamically, so the
+    // digests are complete however many CTAs end up digesting.
+    bool digest_cta = false;
+    if (do_md5) {
+        if (threadIdx.x == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            smid &= kMaxSm - 1;
+            uint32_t *role_w = p.counters + 16 + kMaxSm + smid;
+            uint32_t role;
+            if (atomicAdd(p.counters + 16 + smid, 1u) == 0) {  // first CTA of this SM to report decides for the SM
+                role = (!do_lz4 || atomicAdd(p.counters + 1, 1u) < p.n_md5_sms) ? kRoleDigest : kRoleCompress;
+                atomicExch(role_w, role);
+            } else {
+                unsigned ns = 32;
+                while ((role = ld_relaxed32(role_w)) == 0) {  // the deciding CTA is running: it reported before us
+                    __nanosleep(ns);
+                    if (ns < 1024) ns <<= 1;
+                }
+            }
+            ctl->role = role;
+        }
+        __syncthreads();
+        digest_cta = ctl->role == kRoleDigest;
+    }
+    if (digest_cta) {
         if (warp < kMd5WarpsPerCta) {
-            for (uint32_t g = warp * p.n_md5_ctas + blockIdx.x; g < p.n_groups; g += p.n_md5_ctas * kMd5WarpsPerCta) {
+            for (;;) {
+                uint32_t g = 0;
+                if (lane == 0) g = atomicAdd(p.counters + 2, 1u);  // longest chunks first (md5_order)
+                g = __shfl_sync(kFull, g, 0);
+                if (g >= p.n_groups) break;
                 const uint32_t c = p.md5_order[g * 32 + lane];
                 const bool active = c != 0xffffffffu;
                 const uint8_t *src = nullptr;
@@ -358,9 +395,9 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 }
                 const uint32_t si = my_seq % kRing, ph = (my_seq / kRing) & 1u;
                 bool got = true;
-                // Waiting for a segment must not cost issue slots: mbarrier.try_wait's hardware suspend ends at EVERY barrier
-                // event in the CTA (a few dozen ns apart here), which made the waiting loops a quarter of all instructions
-                // issued (profiles/README.md, r2_27).  Sleep with a doubling period instead.
+                // (mbarrier.try_wait's hardware suspend ends at every barrier event in the CTA, a few dozen ns apart here, so the
+                // waiting loops are a quarter of the instructions issued -- but replacing them with timed sleeps gained
+                // nothing (r2_29: 115.9 vs 116.3 GB/s): the issue slots they take are not the ones the parsers lack.)
                 unsigned ns = 32;
                 while (!(kWaitNs ? mbar_test_wait(&ctl->full[si], ph) : mbar_try_wait_hint(&ctl->full[si], ph, 1000u))) {
                     if (atomicAdd(const_cast<uint32_t *>(&ctl->block_end_seq), 0u) <= my_seq) {  // no such segment in this block: keep the claim
@@ -825,7 +862,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_desc, nc * sizeof(ChunkDesc)));
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMalloc(&s.d_counters, 64));
+    CK(ctx, cudaMalloc(&s.d_counters, kCountersBytes));
     CK(ctx, cudaMalloc(&s.d_scratch, (size_t)ctx->sm_count * kCtasPerSm * kScratchBytes));
     CK(ctx, cudaMallocHost(&s.h_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMalloc(&s.d_dchunks, nc * sizeof(DecChunk)));
@@ -1032,7 +1069,7 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
         CK(ctx, cudaEventRecord(s.ev_h2d, meta_st));  // input (enqueued earlier on meta_st) + metadata have landed
         CK(ctx, cudaStreamWaitEvent(st, s.ev_h2d, 0));
     }
-    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, kCountersBytes, st));
     CK(ctx, cudaMemsetAsync(s.d_progress, 0, (ng + 1) * sizeof(uint32_t), st));
     memset(s.h_outlen, 0, n * sizeof(uint64_t));  // host-side clear (mapped memory; the slot is idle here)
     memset(s.h_md5, 0, (size_t)n * 16);
@@ -1049,8 +1086,8 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     p.n_chunks = n;
     p.n_groups = ng;
     const uint32_t grid = (uint32_t)ctx->sm_count * kCtasPerSm;
-    // digest CTAs: 4 groups (one per SM sub-partition) each; with few groups spread them one per CTA first
-    p.n_md5_ctas = (flags & SKY_F_MD5) ? std::min(grid, std::max((ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta, std::min(ng, (uint32_t)ctx->sm_count / 4))) : 0;
+    // digest SMs: 8 MD5 warps each (two per scheduler); the rest of the GPU compresses.  (MD5 alone: every SM may digest.)
+    p.n_md5_sms = (flags & SKY_F_MD5) ? std::min((uint32_t)ctx->sm_count, (ng + 2 * kMd5WarpsPerCta - 1) / (2 * kMd5WarpsPerCta)) : 0;
     p.rows = rows;
     p.flags = flags;
     CK(ctx, cudaEventRecord(s.ev_k0, st));
