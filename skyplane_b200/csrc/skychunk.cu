@@ -69,7 +69,7 @@ constexpr uint32_t kLoadPiece = 8192;     // bytes per bulk copy of the block lo
 constexpr int kCtasPerSm = 2;             // fused kernel: 2 x ~110 KiB of shared memory per SM
 constexpr uint32_t kMaxSm = 512;          // %smid values the role table covers (B200: 148 SMs)
 constexpr uint32_t kCountersBytes = (16 + 2 * kMaxSm) * 4;
-constexpr uint32_t kRoleCompress = 1, kRoleDigest = 2;
+constexpr uint32_t kRoleCompress = 1, kRoleDigest = 2, kRoleDone = 3;
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
 
@@ -86,6 +86,7 @@ struct Ctl {
     BlockDesc desc[2];              // by block-iteration parity
     uint32_t claim;                 // next segment sequence number a parser may take (runs across blocks)
     uint32_t role;                  // kRoleDigest / kRoleCompress (decided per SM at kernel start)
+    uint32_t *role_word;            // the SM's role word in global memory
     volatile uint32_t block_end_seq;  // sequence number after the current block's last segment (0xffffffff while probing)
     volatile uint32_t nseg;
     volatile uint32_t seg_hit[4];     // per segment (mod 4): OR of its batches' hit masks (decides the stride two segments on)
@@ -125,7 +126,7 @@ struct Params {
     uint8_t *scratch;           // kScratchBytes per CTA: where a block's segments are compressed before its frame offset is known
     uint32_t n_chunks;
     uint32_t n_groups;
-    uint32_t n_md5_sms;         // this many SMs digest (both of their CTAs, 4 MD5 warps each) before they compress
+    uint32_t n_md5_sms;         // this many SMs digest (one CTA with 4 MD5 warps, the other CTA parked) before they compress
     uint32_t rows;  // max(1, max nblk)
     uint32_t flags;
 };
@@ -208,7 +209,8 @@ __device__ __forceinline__ void claim_block(const Params &p, BlockDesc *d, bool 
 }
 
 // Fused LZ4-frame + MD5 kernel.  Grid = 2 CTAs per SM, kWarps warps each.
-//   digest CTAs (both CTAs of the first n_md5_sms SMs to report): warps 0..3 each carry one MD5 group (32 chunks, lane = chunk, md5.cuh) at a time;
+//   digest CTAs (one CTA on each of the first n_md5_sms SMs to report; its neighbour waits): warps 0..3 each carry one MD5 group
+//       (32 chunks, lane = chunk, md5.cuh) at a time;
 //       when the groups are done the CTA joins the compressors.
 //   compressor CTAs: one 64 KiB block at a time -- bulk-load it into shared memory, warp 0 probes, warps 1.. parse
 //       (lz4.cuh), warp 0 plans the block's layout and takes its frame offset from the OFF chain, all warps write it out.
@@ -239,33 +241,48 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     }
     __syncthreads();
 
-    // Digest role per SM, not per CTA: an MD5 warp is a pure dependent chain (one instruction every ~5.4 cycles), so any
-    // compressor warp on its scheduler slows the chain, and a digest CTA's other warps cannot compress (its block buffer
-    // holds the MD5 rings).  The first n_md5_sms SMs to report therefore digest with BOTH their CTAs (8 MD5 warps, two per
-    // scheduler, nothing else on the SM); every other SM compresses from the start.  Groups are claimed dynamically, so the
-    // digests are complete however many CTAs end up digesting.
+    // Digest role per SM, not per CTA.  One MD5 warp keeps its scheduler's issue port ~92 % busy (the chain plus the
+    // off-chain message adds and staging), so it wants a sub-partition to itself: two MD5 warps on one scheduler run at half
+    // speed each (r2_30), and compressor warps next to it slow the chain the whole batch waits for.  So the first n_md5_sms
+    // SMs to report are digest SMs: the first CTA there runs 4 MD5 warps (one per scheduler), its neighbour stays parked
+    // until that CTA's groups are done; every other SM compresses from the start.  (Round 2's first arrangement put one MD5
+    // warp into each of 32 CTAs: 32 of 296 block buffers idle for the whole kernel; now 8 of 148 SMs.)  Groups are claimed
+    // dynamically, so the digests are complete however the CTAs land.
     bool digest_cta = false;
+    uint32_t *role_w = nullptr;
     if (do_md5) {
         if (threadIdx.x == 0) {
             uint32_t smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             smid &= kMaxSm - 1;
-            uint32_t *role_w = p.counters + 16 + kMaxSm + smid;
+            uint32_t *rw = p.counters + 16 + kMaxSm + smid;
             uint32_t role;
             if (atomicAdd(p.counters + 16 + smid, 1u) == 0) {  // first CTA of this SM to report decides for the SM
-                role = (!do_lz4 || atomicAdd(p.counters + 1, 1u) < p.n_md5_sms) ? kRoleDigest : kRoleCompress;
-                atomicExch(role_w, role);
+                role = atomicAdd(p.counters + 1, 1u) < p.n_md5_sms ? kRoleDigest : kRoleCompress;
+                atomicExch(rw, role);
             } else {
                 unsigned ns = 32;
-                while ((role = ld_relaxed32(role_w)) == 0) {  // the deciding CTA is running: it reported before us
+                while ((role = ld_relaxed32(rw)) == 0) {  // the deciding CTA is running: it reported before us
                     __nanosleep(ns);
                     if (ns < 1024) ns <<= 1;
                 }
+                if (role == kRoleDigest) {  // neighbour of a digest CTA: stay out of its schedulers' way until it is done
+                    role = kRoleCompress;
+                    if (do_lz4) {
+                        ns = 1024;
+                        while (ld_relaxed32(rw) != kRoleDone) {
+                            __nanosleep(ns);
+                            if (ns < 16384) ns <<= 1;
+                        }
+                    }
+                }
             }
             ctl->role = role;
+            ctl->role_word = rw;
         }
         __syncthreads();
         digest_cta = ctl->role == kRoleDigest;
+        role_w = ctl->role_word;
     }
     if (digest_cta) {
         if (warp < kMd5WarpsPerCta) {
@@ -290,8 +307,8 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 __syncwarp();
             }
         }
-        if (!do_lz4) return;
-        __syncthreads();  // the rings overlapped the block buffer
+        __syncthreads();  // (the rings overlapped the block buffer)
+        if (threadIdx.x == 0) atomicExch(role_w, kRoleDone);  // the parked neighbour may compress now
     }
     if (!do_lz4) return;
 
@@ -1086,8 +1103,9 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     p.n_chunks = n;
     p.n_groups = ng;
     const uint32_t grid = (uint32_t)ctx->sm_count * kCtasPerSm;
-    // digest SMs: 8 MD5 warps each (two per scheduler); the rest of the GPU compresses.  (MD5 alone: every SM may digest.)
-    p.n_md5_sms = (flags & SKY_F_MD5) ? std::min((uint32_t)ctx->sm_count, (ng + 2 * kMd5WarpsPerCta - 1) / (2 * kMd5WarpsPerCta)) : 0;
+    // digest SMs: 4 MD5 warps each (one per scheduler); the rest of the GPU compresses.  MD5 alone: every SM may digest.
+    p.n_md5_sms = !(flags & SKY_F_MD5) ? 0 : !(flags & SKY_F_LZ4) ? (uint32_t)ctx->sm_count
+                : std::min((uint32_t)ctx->sm_count, (ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta);
     p.rows = rows;
     p.flags = flags;
     CK(ctx, cudaEventRecord(s.ev_k0, st));
