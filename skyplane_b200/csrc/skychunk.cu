@@ -67,9 +67,6 @@ constexpr int kMd5WarpsPerCta = 4;        // digest CTAs run 4 MD5 groups (one p
 constexpr uint32_t kRingBytes = SKY_MD5_SLOTS * 2048;  // MD5 staging ring: slots x 64 B x 32 lanes
 constexpr uint32_t kLoadPiece = 8192;     // bytes per bulk copy of the block load
 constexpr int kCtasPerSm = 2;             // fused kernel: 2 x ~110 KiB of shared memory per SM
-constexpr uint32_t kMaxSm = 512;          // %smid values the role table covers (B200: 148 SMs)
-constexpr uint32_t kCountersBytes = (16 + 2 * kMaxSm) * 4;
-constexpr uint32_t kRoleCompress = 1, kRoleDigest = 2, kRoleDone = 3;
 constexpr int kOffBits = 40;
 constexpr uint64_t kOffMask = (1ull << kOffBits) - 1;
 
@@ -85,8 +82,6 @@ struct Ctl {
     uint64_t full[kRing], empty[kRing];
     BlockDesc desc[2];              // by block-iteration parity
     uint32_t claim;                 // next segment sequence number a parser may take (runs across blocks)
-    uint32_t role;                  // kRoleDigest / kRoleCompress (decided per SM at kernel start)
-    uint32_t *role_word;            // the SM's role word in global memory
     volatile uint32_t block_end_seq;  // sequence number after the current block's last segment (0xffffffff while probing)
     volatile uint32_t nseg;
     volatile uint32_t seg_hit[4];     // per segment (mod 4): OR of its batches' hit masks (decides the stride two segments on)
@@ -121,12 +116,11 @@ struct Params {
     uint32_t *md5_progress;     // per MD5 group: 0 = not started, else 1 + 64 KiB rows consumed (0xffffffff = done)
     uint64_t *out_len;          // per chunk frame length
     uint8_t *md5_out;           // 16 bytes per chunk
-    uint32_t *counters;         // [0] = LZ4 work counter, [1] = digest-SM tickets, [2] = MD5 group counter,
-                                // [16 + smid] = CTAs that reported from that SM, [16 + kMaxSm + smid] = the SM's role
+    uint32_t *counters;         // [0] = LZ4 work counter
     uint8_t *scratch;           // kScratchBytes per CTA: where a block's segments are compressed before its frame offset is known
     uint32_t n_chunks;
     uint32_t n_groups;
-    uint32_t n_md5_sms;         // this many SMs digest (one CTA with 4 MD5 warps, the other CTA parked) before they compress
+    uint32_t n_md5_ctas;        // CTAs 0..n_md5_ctas-1 digest (4 groups each at a time) before they compress
     uint32_t rows;  // max(1, max nblk)
     uint32_t flags;
 };
@@ -209,8 +203,7 @@ __device__ __forceinline__ void claim_block(const Params &p, BlockDesc *d, bool 
 }
 
 // Fused LZ4-frame + MD5 kernel.  Grid = 2 CTAs per SM, kWarps warps each.
-//   digest CTAs (one CTA on each of the first n_md5_sms SMs to report; its neighbour waits): warps 0..3 each carry one MD5 group
-//       (32 chunks, lane = chunk, md5.cuh) at a time;
+//   digest CTAs (blockIdx < n_md5_ctas): warps 0..3 each carry one MD5 group (32 chunks, lane = chunk, md5.cuh) at a time;
 //       when the groups are done the CTA joins the compressors.
 //   compressor CTAs: one 64 KiB block at a time -- bulk-load it into shared memory, warp 0 probes, warps 1.. parse
 //       (lz4.cuh), warp 0 plans the block's layout and takes its frame offset from the OFF chain, all warps write it out.
@@ -241,56 +234,9 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
     }
     __syncthreads();
 
-    // Digest role per SM, not per CTA.  One MD5 warp keeps its scheduler's issue port ~92 % busy (the chain plus the
-    // off-chain message adds and staging), so it wants a sub-partition to itself: two MD5 warps on one scheduler run at half
-    // speed each (r2_30), and compressor warps next to it slow the chain the whole batch waits for.  So the first n_md5_sms
-    // SMs to report are digest SMs: the first CTA there runs 4 MD5 warps (one per scheduler), its neighbour stays parked
-    // until that CTA's groups are done; every other SM compresses from the start.  (Round 2's first arrangement put one MD5
-    // warp into each of 32 CTAs: 32 of 296 block buffers idle for the whole kernel; now 8 of 148 SMs.)  Groups are claimed
-    // dynamically, so the digests are complete however the CTAs land.
-    bool digest_cta = false;
-    uint32_t *role_w = nullptr;
-    if (do_md5) {
-        if (threadIdx.x == 0) {
-            uint32_t smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            smid &= kMaxSm - 1;
-            uint32_t *rw = p.counters + 16 + kMaxSm + smid;
-            uint32_t role;
-            if (atomicAdd(p.counters + 16 + smid, 1u) == 0) {  // first CTA of this SM to report decides for the SM
-                role = atomicAdd(p.counters + 1, 1u) < p.n_md5_sms ? kRoleDigest : kRoleCompress;
-                atomicExch(rw, role);
-            } else {
-                unsigned ns = 32;
-                while ((role = ld_relaxed32(rw)) == 0) {  // the deciding CTA is running: it reported before us
-                    __nanosleep(ns);
-                    if (ns < 1024) ns <<= 1;
-                }
-                if (role == kRoleDigest) {  // neighbour of a digest CTA: stay out of its schedulers' way until it is done
-                    role = kRoleCompress;
-                    if (do_lz4) {
-                        ns = 1024;
-                        while (ld_relaxed32(rw) != kRoleDone) {
-                            __nanosleep(ns);
-                            if (ns < 16384) ns <<= 1;
-                        }
-                    }
-                }
-            }
-            ctl->role = role;
-            ctl->role_word = rw;
-        }
-        __syncthreads();
-        digest_cta = ctl->role == kRoleDigest;
-        role_w = ctl->role_word;
-    }
-    if (digest_cta) {
+    if (do_md5 && blockIdx.x < p.n_md5_ctas) {
         if (warp < kMd5WarpsPerCta) {
-            for (;;) {
-                uint32_t g = 0;
-                if (lane == 0) g = atomicAdd(p.counters + 2, 1u);  // longest chunks first (md5_order)
-                g = __shfl_sync(kFull, g, 0);
-                if (g >= p.n_groups) break;
+            for (uint32_t g = warp * p.n_md5_ctas + blockIdx.x; g < p.n_groups; g += p.n_md5_ctas * kMd5WarpsPerCta) {
                 const uint32_t c = p.md5_order[g * 32 + lane];
                 const bool active = c != 0xffffffffu;
                 const uint8_t *src = nullptr;
@@ -307,8 +253,8 @@ __global__ void __launch_bounds__(kThreads, 2) sky_fused_kernel(const Params p) 
                 __syncwarp();
             }
         }
-        __syncthreads();  // (the rings overlapped the block buffer)
-        if (threadIdx.x == 0) atomicExch(role_w, kRoleDone);  // the parked neighbour may compress now
+        if (!do_lz4) return;
+        __syncthreads();  // the rings overlapped the block buffer
     }
     if (!do_lz4) return;
 
@@ -879,7 +825,7 @@ static int alloc_meta(sky_ctx *ctx, Slot &s, uint32_t max_chunks) {
     CK(ctx, cudaMalloc(&s.d_desc, nc * sizeof(ChunkDesc)));
     CK(ctx, cudaMalloc(&s.d_order, ng * sizeof(uint32_t)));
     CK(ctx, cudaMalloc(&s.d_chain, nc * sizeof(uint64_t)));
-    CK(ctx, cudaMalloc(&s.d_counters, kCountersBytes));
+    CK(ctx, cudaMalloc(&s.d_counters, 64));
     CK(ctx, cudaMalloc(&s.d_scratch, (size_t)ctx->sm_count * kCtasPerSm * kScratchBytes));
     CK(ctx, cudaMallocHost(&s.h_dchunks, nc * sizeof(DecChunk)));
     CK(ctx, cudaMalloc(&s.d_dchunks, nc * sizeof(DecChunk)));
@@ -1086,7 +1032,7 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
         CK(ctx, cudaEventRecord(s.ev_h2d, meta_st));  // input (enqueued earlier on meta_st) + metadata have landed
         CK(ctx, cudaStreamWaitEvent(st, s.ev_h2d, 0));
     }
-    CK(ctx, cudaMemsetAsync(s.d_counters, 0, kCountersBytes, st));
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 64, st));
     CK(ctx, cudaMemsetAsync(s.d_progress, 0, (ng + 1) * sizeof(uint32_t), st));
     memset(s.h_outlen, 0, n * sizeof(uint64_t));  // host-side clear (mapped memory; the slot is idle here)
     memset(s.h_md5, 0, (size_t)n * 16);
@@ -1103,9 +1049,11 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     p.n_chunks = n;
     p.n_groups = ng;
     const uint32_t grid = (uint32_t)ctx->sm_count * kCtasPerSm;
-    // digest SMs: 4 MD5 warps each (one per scheduler); the rest of the GPU compresses.  MD5 alone: every SM may digest.
-    p.n_md5_sms = !(flags & SKY_F_MD5) ? 0 : !(flags & SKY_F_LZ4) ? (uint32_t)ctx->sm_count
-                : std::min((uint32_t)ctx->sm_count, (ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta);
+    // digest CTAs: 4 groups (one per SM sub-partition) each; with few groups spread them one per CTA first.  (Tried in
+    // r2_30 / r2_31: whole digest SMs -- 4 or 8 MD5 warps on a few SMs, nothing else there -- so that fewer block buffers
+    // sit idle.  With 8 or 16 MiB chunks the MD5 warps then ran at half their chain rate (0.061 GB/s per chunk; with 1 MiB
+    // chunks at the full 0.118), so the spread-out arrangement stays.)
+    p.n_md5_ctas = (flags & SKY_F_MD5) ? std::min(grid, std::max((ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta, std::min(ng, (uint32_t)ctx->sm_count / 4))) : 0;
     p.rows = rows;
     p.flags = flags;
     CK(ctx, cudaEventRecord(s.ev_k0, st));

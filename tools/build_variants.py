@@ -8,10 +8,11 @@ sys.path.insert(0, str(ROOT))
 from skyplane_b200 import build  # noqa: E402
 
 VARIANTS = {
-    "pa10": {"SKY_PARSERS": 10},
-    "pa11_r2": {"SKY_PARSERS": 11, "SKY_RING_EXTRA": 2},
-    "pa10_lit32": {"SKY_PARSERS": 10, "SKY_COOP_LIT": 32},
-    "pa10_lit8": {"SKY_PARSERS": 10, "SKY_COOP_LIT": 8},
+    "pa10_r3": {"SKY_PARSERS": 10, "SKY_RING_EXTRA": 3},
+    "pa12_r2": {"SKY_PARSERS": 12, "SKY_RING_EXTRA": 2},  # the default build
+    "pa13_r1": {"SKY_PARSERS": 13, "SKY_RING_EXTRA": 1},
+    "wait1024": {"SKY_WAIT_NS": 1024},
+    "pace1": {"SKY_PACE_LEAD": 1},
 }
 
 if __name__ == "__main__":
