@@ -150,8 +150,8 @@ def _twin_opts():
 
 def test_frames_equal_sequential_twin(ctx):
     """The warp-parallel parse is specified by a sequential program (tools/lz4_tile_model.c): same table rule, same tile
-    parse, same emission.  Frames must be byte-identical -- this pins every lane-level shortcut of the kernel (match.any
-    ordering, fused forward/backward compare, per-segment parsers, carried literals, batched emission, stride doubling) to plain sequential semantics."""
+    parse, same emission.  Frames must be byte-identical -- this pins every lane-level shortcut of the kernel (group-wise
+    table lookups with atomic-max updates, in-group hash compares, fused forward/backward compare, per-segment parsers, carried literals, batched emission, stride doubling) to plain sequential semantics."""
     tm, o = _twin_opts()
     a = RNG.bytes(1000)
     datas = [kinds(n)[k] for n in (13, 300, 4096, 65536, 65537, 200000) for k in ("zeros", "period7", "text", "half", "random")]
