@@ -1053,7 +1053,17 @@ static int launch_batch(sky_ctx *ctx, Slot &s, cudaStream_t st, cudaStream_t met
     // r2_30 / r2_31: whole digest SMs -- 4 or 8 MD5 warps on a few SMs, nothing else there -- so that fewer block buffers
     // sit idle.  With 8 or 16 MiB chunks the MD5 warps then ran at half their chain rate (0.061 GB/s per chunk; with 1 MiB
     // chunks at the full 0.118), so the spread-out arrangement stays.)
-    p.n_md5_ctas = (flags & SKY_F_MD5) ? std::min(grid, std::max((ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta, std::min(ng, (uint32_t)ctx->sm_count / 4))) : 0;
+    {
+        // MD5 warps per digest CTA while the groups are few: 1 = one warp in each of up to sm_count / 4 CTAs (default);
+        // SKYCHUNK_MD5_WARPS=2 packs two per CTA so that half as many block buffers sit idle in the fused kernel (tuning knob)
+        static const uint32_t md5_warps = [] {
+            const char *e = getenv("SKYCHUNK_MD5_WARPS");
+            const int v = e ? atoi(e) : 1;
+            return (uint32_t)(v >= 1 && v <= kMd5WarpsPerCta ? v : 1);
+        }();
+        p.n_md5_ctas = (flags & SKY_F_MD5) ? std::min(grid, std::max((ng + kMd5WarpsPerCta - 1) / kMd5WarpsPerCta,
+                                                                     std::min((ng + md5_warps - 1) / md5_warps, (uint32_t)ctx->sm_count / 4))) : 0;
+    }
     p.rows = rows;
     p.flags = flags;
     CK(ctx, cudaEventRecord(s.ev_k0, st));
