@@ -128,7 +128,7 @@ class GatewayCompressHash(GatewayOperator):
         max_batch_bytes: int = 512 << 20,
         n_gpus: Optional[int] = None,
         keep_frames_on_disk: bool = True,
-        read_threads: int = 8,
+        read_threads: int = 12,
         ingest_read_local: bool = True,
         e2ee_key_bytes: Optional[bytes] = None,
         sink=None,
@@ -238,47 +238,64 @@ class GatewayCompressHash(GatewayOperator):
         except FileNotFoundError:
             return path, None, False
 
-    def _launch(self, reqs: List[ChunkRequest]):
-        """Stage as many of `reqs` as fit one slot and launch them.
-        -> (slot or None, launched indices, not-ready indices, leftover indices)"""
+    def _stage_reads(self, reqs: List[ChunkRequest]):
+        """Reserve room in a free staging slot for as many of `reqs` as fit and START reading them into pinned memory
+        (thread pool; file -> pinned copies release the GIL).  Nothing here touches the GPU.
+        -> (slot or None, jobs [(index, future)], not-ready indices, leftover indices)"""
         stage = self._get_stage()
         slot = stage.begin()
-        launched, not_ready, leftover, jobs = [], [], [], []
+        not_ready, leftover, jobs = [], [], []
         for i, r in enumerate(reqs):
             chunk = r.chunk
             n = chunk.chunk_length_bytes
             if n > stage.max_batch_bytes:
+                for _, fut in jobs:
+                    fut.result()  # (reads into the slot we are about to give back must be over first)
                 stage.release(slot)
                 if len(stage._free) < len(stage._slots):  # batches in flight: come back when they have been collected
                     return None, [], [], list(range(len(reqs)))
                 self._grow_stage(n)
                 if n > self._get_stage().max_batch_bytes:
                     raise ValueError(f"chunk {chunk.chunk_id} ({n} B) exceeds what the stage can be grown to")
-                return self._launch(reqs)
+                return self._stage_reads(reqs)
             path, offset, ready = self._source_of(r)
             if not ready:
                 not_ready.append(i)
             elif not stage.fits(slot, n):
                 leftover.append(i)
             else:
-                jobs.append((i, path, slot.reserve(n), n, offset))
-        if jobs:
-            # file -> pinned memory copies release the GIL: read the batch with a few threads
-            if self._readers is None:
-                from concurrent.futures import ThreadPoolExecutor
+                if self._readers is None:
+                    from concurrent.futures import ThreadPoolExecutor
 
-                self._readers = ThreadPoolExecutor(max_workers=self.read_threads)
-            oks = list(self._readers.map(lambda j: self._read_into(j[1], j[2], j[3], j[4]), jobs))
-            if not all(oks):  # a file changed under us: retry the whole batch later rather than hash partial data
-                stage.release(slot)
-                return None, [], [j[0] for j in jobs] + not_ready, leftover
-            launched = [j[0] for j in jobs]
-            stage.launch(slot, compress=self.use_compression, encrypt=self.e2ee_key_bytes is not None)
-            return slot, launched, not_ready, leftover
+                    self._readers = ThreadPoolExecutor(max_workers=self.read_threads)
+                jobs.append((i, self._readers.submit(self._read_into, path, slot.reserve(n), n, offset)))
+        if jobs:
+            return slot, jobs, not_ready, leftover
         stage.release(slot)
         if leftover:
             raise RuntimeError("staging slot cannot hold a single chunk")
         return None, [], not_ready, leftover
+
+    def _launch_staged(self, slot, jobs) -> bool:
+        """Wait for the reads of a staged batch and launch it.  False: a file changed under us -- the slot is given back and
+        the whole batch must be retried later rather than hash partial data."""
+        stage = self._get_stage()
+        if not all([fut.result() for _, fut in jobs]):
+            stage.release(slot)
+            return False
+        stage.launch(slot, compress=self.use_compression, encrypt=self.e2ee_key_bytes is not None)
+        return True
+
+    def _launch(self, reqs: List[ChunkRequest]):
+        """Stage as many of `reqs` as fit one slot, read them and launch them (synchronously).
+        -> (slot or None, launched indices, not-ready indices, leftover indices)"""
+        slot, jobs, not_ready, leftover = self._stage_reads(reqs)
+        if slot is None:
+            return None, [], not_ready, leftover
+        idx = [i for i, _ in jobs]
+        if not self._launch_staged(slot, jobs):
+            return None, [], idx + not_ready, leftover
+        return slot, idx, not_ready, leftover
 
     def _finish(self, slot, reqs: List[ChunkRequest]):
         """Collect a launched batch: sets md5_hash, hands the payloads on (socket sink, or payload files), attaches the
@@ -330,44 +347,60 @@ class GatewayCompressHash(GatewayOperator):
             self.output_queue.put_many(reqs)
 
     def worker_loop(self, worker_id: int, *args):
-        """Batch-draining, double-buffered loop with the reference's logging / error conventions: while the GPU
-        works on one batch the next one is read from the chunk files into the other staging slot."""
+        """Batch-draining loop with the reference's logging / error conventions.  Three things overlap: the chunk files of
+        batch k+1 are read into a free staging slot by the reader threads while batch k is on the GPU (several batches are)
+        and while this thread waits for the oldest batch's payloads to come back (`_finish`)."""
         self.worker_id = worker_id
         inflight = []  # [(slot, reqs)] oldest first
-        backlog: List[ChunkRequest] = []  # dequeued but not yet launched (did not fit the slot)
+        reading = None  # (slot, jobs, cand): a batch whose chunk files are being read into its slot
+        backlog: List[ChunkRequest] = []  # dequeued but not yet staged (did not fit the slot)
         try:
             while self._running(worker_id):
                 try:
-                    stage_free = self._stage is None or bool(self._stage._free)
-                    if backlog and inflight and max(r.chunk.chunk_length_bytes for r in backlog) > self.max_batch_bytes:
-                        stage_free = False  # an oversize chunk waits for the stage to drain, then the stage is rebuilt
-                    if stage_free:
-                        room = self.max_batch_chunks - len(backlog)
-                        fresh = self.input_queue.get_batch_nowait(room, self.handle) if room > 0 else []
-                        if fresh:
-                            self.chunk_store.log_chunk_states(fresh, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
-                        cand = backlog + fresh
-                        if cand:
-                            slot, launched, not_ready, leftover = self._launch(cand)
-                            if slot is not None:
-                                inflight.append((slot, [cand[k] for k in launched]))
-                            backlog = [cand[k] for k in leftover]
-                            if not_ready:
-                                time.sleep(0.1 if slot is None and not inflight else 0)
-                                for k in not_ready:
-                                    self.input_queue.put(cand[k])
-                            if slot is not None and len(inflight) < self.n_slots:
-                                continue  # try to get a second batch going before blocking on the first
-                    if inflight:
-                        slot, reqs = inflight.pop(0)
+                    progressed = False
+                    if reading is not None and (not inflight or all(fut.done() for _, fut in reading[1])):
+                        slot, jobs, cand = reading
+                        reading = None
+                        progressed = True
+                        if self._launch_staged(slot, jobs):
+                            inflight.append((slot, [cand[i] for i, _ in jobs]))
+                        else:
+                            for i, _ in jobs:
+                                self.input_queue.put(cand[i])
+                    if reading is None:
+                        stage_free = self._stage is None or bool(self._stage._free)
+                        if backlog and inflight and max(r.chunk.chunk_length_bytes for r in backlog) > self.max_batch_bytes:
+                            stage_free = False  # an oversize chunk waits for the stage to drain, then the stage is rebuilt
+                        if stage_free:
+                            room = self.max_batch_chunks - len(backlog)
+                            fresh = self.input_queue.get_batch_nowait(room, self.handle) if room > 0 else []
+                            if fresh:
+                                self.chunk_store.log_chunk_states(fresh, ChunkState.in_progress, operator_handle=self.handle, worker_id=worker_id)
+                            cand = backlog + fresh
+                            if cand:
+                                slot, jobs, not_ready, leftover = self._stage_reads(cand)
+                                if slot is not None:
+                                    reading = (slot, jobs, cand)
+                                    progressed = True
+                                backlog = [cand[k] for k in leftover]
+                                if not_ready:
+                                    time.sleep(0.1 if slot is None and not inflight else 0)
+                                    for k in not_ready:
+                                        self.input_queue.put(cand[k])
+                    if inflight and (reading is None or len(inflight) >= self.n_slots - 1):
+                        slot, reqs = inflight.pop(0)  # (blocks until that batch's payloads are back; the readers keep going)
                         self._finish(slot, reqs)
                         self._complete_many(worker_id, reqs)
-                    elif not backlog:
-                        time.sleep(0.0005)
+                    elif not progressed:
+                        time.sleep(0.0002 if reading is not None else 0.0005)  # reads under way / nothing queued
                 except Exception as e:
                     self._fail(worker_id, e)
-            # drain what is already on the GPU so no accepted chunk is lost on a clean stop
+            # drain what is already staged / on the GPU so no accepted chunk is lost on a clean stop
             if not self.error_event.is_set():
+                if reading is not None:
+                    slot, jobs, cand = reading
+                    if self._launch_staged(slot, jobs):
+                        inflight.append((slot, [cand[i] for i, _ in jobs]))
                 for slot, reqs in inflight:
                     self._finish(slot, reqs)
                     self._complete_many(worker_id, reqs)
