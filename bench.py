@@ -587,7 +587,7 @@ def run_gpu(args):
         barrier()
         if rank == 0:
             cmd = [sys.executable, "-m", "skyplane_b200.harness", "--gpus", str(world), "--chunks", str(args.queue_chunks * world), "--chunk-mib",
-                   str(args.chunk_mib), "--workload", args.workload if args.workload == "random" else "silesia", "--pool", "32", "--batch", "128", "--slots", "3"]
+                   str(args.chunk_mib), "--workload", args.workload if args.workload == "random" else "silesia", "--pool", "32", "--batch", "128", "--slots", "4"]
             env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
             try:
                 out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=str(ROOT), env=env)

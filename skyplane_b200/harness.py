@@ -54,7 +54,7 @@ def run_stream(
     on_done: Optional[Callable[[ChunkRequest], None]] = None,
     warmup_requests: int = 0,
     operator_cls=GatewayCompressHash,
-    n_slots: int = 3,
+    n_slots: int = 4,
 ) -> Dict:
     """Stream ``n_requests`` chunk requests (recycling ``pool_files`` by hard link) through the operator.
 
@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--pool", type=int, default=32)
     ap.add_argument("--workload", choices=["random", "silesia", "mixed"], default="mixed")
     ap.add_argument("--batch", type=int, default=128, help="chunks per kernel launch")
-    ap.add_argument("--slots", type=int, default=3, help="launches in flight per worker")
+    ap.add_argument("--slots", type=int, default=4, help="staging slots per worker (one being read into, the others on the GPU)")
     ap.add_argument("--warmup", type=int, default=-1, help="untimed leading requests (default: 4 batches per GPU)")
     ap.add_argument("--dir", default=None)
     a = ap.parse_args()
