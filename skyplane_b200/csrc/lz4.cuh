@@ -1,38 +1,31 @@
-// lz4.cuh -- warp-per-block LZ4 block compressor for sm_100a.
+// lz4.cuh -- LZ4 block compressor for sm_100a: helpers shared by all formulations, and the CTA-per-block compressor
+// (prober / parser warps over a shared-memory copy of the block) that sky_fused_kernel runs.
 //
 // Replaces, per 64 KiB block, what lz4.frame.compress(data) does inside
 // skyplane/gateway/operators/gateway_operator.py:358-361 (liblz4's level-0 "fast" compressor:
-// single-candidate hash table, greedy, skip acceleration).  The GPU formulation:
-//   * one warp owns one independent 64 KiB block (frame flag B.Indep, so no cross-block state);
-//   * the match table is 4096 x u16 block positions in shared memory (8 KiB per warp);
-//   * each iteration the 32 lanes probe 32 cursor positions (stride = LZ4's skip step, which grows
-//     by one every 64 failed probes), the lowest matching lane wins (greedy = reference order),
-//     the match is extended backwards/forwards cooperatively, and the sequence is emitted.
+// single-candidate hash table, greedy, skip acceleration).  The GPU formulation (details above each part below):
+//   * one CTA owns one independent 64 KiB block at a time (frame flag B.Indep, so no cross-block state);
+//   * the match table is 4096 x (pos16 << 16 | tag16) in shared memory; a probe never reads the candidate's bytes;
+//   * 32 probe slots are one warp instruction; the stride between slots doubles over data without hits;
+//   * parser warps verify and extend the hits of whole segments independently and emit standard LZ4 sequences;
 //   * blocks that do not shrink are stored raw (bit 31 of the block header), like LZ4F_makeBlock.
 // Output is a standard LZ4 block: decodable by lz4.frame.decompress (gateway_receiver.py:196).
+// tools/lz4_tile_model.c is the sequential twin of the parse; frames are byte-identical to it (tests).
 #pragma once
 #include <stdint.h>
 
 namespace sky {
 
 constexpr uint32_t kBlock = 65536;       // BD = 0x40
-constexpr uint32_t kSlot = kBlock + 4;   // worst-case block footprint in the frame (header + raw data)
 #ifndef SKY_LZ4_ENTRIES
 #define SKY_LZ4_ENTRIES 4096
 #endif
-constexpr uint32_t kEntries = SKY_LZ4_ENTRIES;  // match-table entries per warp (u32 each: pos16 | tag16); any multiple of 128
+constexpr uint32_t kEntries = SKY_LZ4_ENTRIES;  // match-table entries per CTA (u32 each: pos16 << 16 | tag16); any multiple of 128
 constexpr uint32_t kTableBytes = kEntries * 4;
 constexpr uint32_t kMinMatch = 4;
 constexpr uint32_t kMfLimit = 12;        // a match must start >= 12 bytes before the block end
 constexpr uint32_t kLastLiterals = 5;    // the last 5 bytes are always literals
 constexpr unsigned kFull = 0xffffffffu;
-
-// ---- unaligned little-endian 32-bit read from global memory (base 4-byte aligned) --------------
-__device__ __forceinline__ uint32_t load32(const uint8_t *base, uint32_t pos) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (pos & ~3u));
-    const uint32_t lo = __ldg(w), hi = __ldg(w + 1);
-    return __funnelshift_r(lo, hi, (pos & 3u) * 8u);
-}
 
 // ---- warp copy: dst and src arbitrarily aligned; regions disjoint, or dst < src (forward move) ----
 // Over-reads at most 3 bytes past src+n (inside the same 4-byte word group); never over-writes.
@@ -134,19 +127,6 @@ __device__ __forceinline__ void warp_copy_stream(uint8_t *dst, const uint8_t *__
     if (lane < (rem & 15u)) dst[done + lane] = src[done + lane];
 }
 
-// Ask L2 to fetch [p, p+bytes) (bytes multiple of 16, p 16-byte aligned); one thread issues it.
-// -DSKY_L2_EVICT_LAST=1 tags the row evict-last so it survives until the MD5 lanes have read it (experiment for the
-// 1.21x DRAM traffic of config 2; off by default, not yet measured).
-__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
-#if SKY_L2_EVICT_LAST
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(policy) : "memory");
-#else
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-#endif
-}
-
 // ---- XXH32 of the frame descriptor (2 or 10 bytes), for the header checksum byte -----------------
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
 __device__ __forceinline__ uint32_t xxh32_small(const uint8_t *p, uint32_t len) {  // len < 16, seed 0
@@ -188,13 +168,6 @@ __device__ __forceinline__ uint32_t write_frame_header(uint8_t *dst, uint64_t n)
 }
 
 // ---- sequence emission ----------------------------------------------------------------------------
-// Bytes a sequence with `ll` literals and match length `ml` (>= 4, or 0 for the final literal run) needs.
-__device__ __forceinline__ uint32_t seq_bytes(uint32_t ll, uint32_t ml) {
-    uint32_t s = 1 + ll + (ll >= 15 ? (ll - 15) / 255 + 1 : 0);
-    if (ml) s += 2 + ((ml - 4) >= 15 ? (ml - 4 - 15) / 255 + 1 : 0);
-    return s;
-}
-
 // Emits token, literal-length bytes, literals, offset, match-length bytes.  All lanes call it with
 // warp-uniform arguments; returns the new output cursor.
 __device__ __forceinline__ uint32_t emit_seq(uint8_t *out, uint32_t op, const uint8_t *src, uint32_t anchor, uint32_t ll,

@@ -1,24 +1,23 @@
 // skychunk.cu -- fused LZ4-frame + MD5 chunk stage for B200 (sm_100a) and its C ABI (include/skychunk.h).
 //
-// One persistent kernel per batch, one CTA per SM, 24 warps per CTA, roles per warp:
-//   * MD5 warps  : 32 chunks per warp, lane = chunk (md5.cuh).  Statically spread: MD5 slot
-//                  s = warp*gridDim + blockIdx takes groups s, s+4*gridDim, ... so 32 groups land on
-//                  32 different SMs.  An MD5 chain is latency bound (3 dependent ALU ops per step).
-//   * LZ4 warps  : one 64 KiB block per work item (lz4.cuh), claimed from a global atomic counter in
-//                  row-major order (block row j of every chunk, then row j+1 ...).
-// Output placement (single pass, no compaction kernel): block j is compressed into its WORST-CASE
-// slot (15 + j*65540) inside the chunk's output region.  Two per-chunk words then order the blocks:
-//   OFF  = (next block index, frame offset of that block): a prefix sum handed from block j-1 to block j
-//          as soon as j-1 knows its own size -- before any data is moved, so offsets race down the chain;
-//   FREE = number of leading blocks whose slots no longer hold unmoved bytes.
-// Block j waits for OFF (its final position), publishes OFF for j+1, waits for FREE >= j (nobody before it
-// still needs bytes that its destination may overlap), then: compressed + moved -> slides its bytes left
-// (forward move) and sets FREE = j+1; stored raw (or not moved) -> sets FREE = j+1 at once and copies the
-// input straight to the final place off the chain.  Incompressible data therefore costs exactly one read
-// of the input and one write of the output.  The last block's warp writes the EndMark and the frame length.
+// One persistent kernel per batch (sky_fused_kernel), two CTAs per SM, 14 warps per CTA, one role per CTA at a time:
+//   * digest CTAs : the first few CTAs carry the MD5 groups -- 32 chunks per warp, lane = chunk (md5.cuh), one MD5 warp
+//                   per CTA while the groups are few.  An MD5 chain is latency bound (3 dependent ALU ops per step, one
+//                   64-byte block per 1042 cycles) and keeps its scheduler's issue port busy; when a CTA's groups are done
+//                   it joins the compressors.
+//   * compressor CTAs : one 64 KiB block at a time, claimed from a global atomic counter in row-major order (block row j of
+//                   every chunk, then row j+1 ...): bulk-load the block into shared memory, warps 0-1 probe, warps 2-13
+//                   parse segment by segment into an L2-resident scratch (lz4.cuh), warp 0 plans the block's layout.
+// Output placement (single pass, no compaction kernel): a block's final place in the frame is only known when every block
+// before it has been sized, so one per-chunk word orders the blocks:
+//   OFF = (next block index << 40) | frame offset of that block: a prefix sum handed from block j-1 to block j as soon as
+//         j-1 knows its compressed size -- before it has written a byte, so offsets race down the chain.
+// Block j sizes itself from its segments' records, waits for OFF (its final position), publishes OFF for j+1 and then
+// writes its bytes to the final place exactly once (stored blocks straight from the input).  The last block's CTA writes
+// the EndMark and the frame length.
 //
-// HBM-read sharing: when MD5 is the slower stage, LZ4 work for block row j is released only when the MD5
-// lanes are within one row of it (per-group progress word), so the lanes find the row in L2.
+// HBM-read sharing: when MD5 is the slower stage, LZ4 work for block row j is released only when the MD5 lanes have entered
+// that row (per-group progress word), so a row is pulled from HBM once and the lanes find it in L2.
 //
 // Host side: sky_ctx owns a stream, pinned + device metadata arrays, and (optionally) per-slot input /
 // output slabs for the host-buffer path (H2D -> kernel -> D2H on one stream per slot).
